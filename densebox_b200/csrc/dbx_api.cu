@@ -1,0 +1,48 @@
+// densebox_b200 — C ABI (see include/densebox_b200.h). Plain pointers and sizes only; every call is asynchronous
+// on the given stream, allocates nothing, and returns 0 or an error code. No exceptions cross this boundary.
+#include "../../include/densebox_b200.h"
+#include "dbx_common.h"
+
+using namespace dbx;
+
+static Act mk_act(const void* p, int N, int H, int W, int C, int cs, int coff) {
+  Act a;
+  a.ptr = const_cast<void*>(p); a.N = N; a.H = H; a.W = W; a.C = C; a.cs = cs; a.coff = coff;
+  return a;
+}
+
+extern "C" {
+
+int dbx_version(void) { return 100; }
+
+const char* dbx_error_string(int code) {
+  switch (code) {
+    case DBX_OK: return "ok";
+    case DBX_ERR_ARG: return "dbx: invalid argument (shape/alignment/null)";
+    case DBX_ERR_DRIVER: return "dbx: cuTensorMapEncodeTiled not resolvable (no CUDA driver?)";
+    case DBX_ERR_TMAP: return "dbx: cuTensorMapEncodeTiled failed";
+    case DBX_ERR_WORKSPACE: return "dbx: workspace too small";
+    case DBX_ERR_STATE: return "dbx: invalid call order";
+    default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "dbx: unknown error";
+  }
+}
+
+int dbx_conv_fprop(const void* x, int N, int H, int W, int cin, int x_cs, int x_coff, const void* wk, int R, int S,
+                   int pad, int cout, const float* bias, int relu, const void* aux, int aux_cs, int aux_coff,
+                   int aux_mode, void* out, int out_cs, int out_coff, int out_fp32, int block_n, void* stream) {
+  Act ax = mk_act(x, N, H, W, cin, x_cs, x_coff);
+  Act ao = mk_act(out, N, H + 2 * pad - R + 1, W + 2 * pad - S + 1, cout, out_cs, out_coff);
+  ConvEpilogue e;
+  e.bias = bias; e.relu = relu; e.aux = aux; e.aux_cs = aux_cs; e.aux_coff = aux_coff; e.aux_mode = aux_mode;
+  e.out_fp32 = out_fp32;
+  return conv_fprop(ax, wk, R, S, pad, ao, e, block_n, (cudaStream_t)stream);
+}
+
+int dbx_conv_wgrad(const void* x, int N, int H, int W, int cin, int x_cs, int x_coff, const void* dy, int cout,
+                   int dy_cs, int dy_coff, int R, int S, int pad, float* dw, int block_n, void* stream) {
+  Act ax = mk_act(x, N, H, W, cin, x_cs, x_coff);
+  Act ad = mk_act(dy, N, H + 2 * pad - R + 1, W + 2 * pad - S + 1, cout, dy_cs, dy_coff);
+  return conv_wgrad(ax, ad, R, S, pad, dw, block_n, (cudaStream_t)stream);
+}
+
+}  // extern "C"

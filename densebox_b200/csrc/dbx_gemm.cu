@@ -1,0 +1,515 @@
+// densebox_b200 — the two tcgen05 contraction kernels of the DenseBox hot path.
+//
+//   conv_fprop : implicit-GEMM convolution, rows = output pixels (a tw x th x tn box fetched by one 4-D TMA per
+//                filter tap and 64-channel slice, zero padding = TMA out-of-bounds fill), cols = output channels.
+//                A and B are K-major SWIZZLE_128B tiles, D lives in TMEM (double-buffered), one elected thread
+//                issues tcgen05.mma, four epilogue warps drain TMEM -> bias/ReLU/mask -> global.
+//                Used for every 3x3/5x5/1x1 convolution forward AND for every data-gradient (dgrad = fprop with
+//                the flipped/transposed filter).  Replaces the cuDNN calls behind DenseBox.py:185-224.
+//   conv_wgrad : weight gradient, rows = output channels, cols = (tap, input channel), K = pixels.  Both operands
+//                are MN-major SWIZZLE_128B tiles (the NHWC tensors are used as they lie), split-K over pixel
+//                boxes, fp32 red.add epilogue.  Replaces the cuDNN wgrad behind loss.backward() (DenseBox.py:2925).
+//
+// Both kernels are persistent (one CTA per SM, static round-robin tile schedule) and warp-specialised:
+//   warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue.
+#include "dbx_common.h"
+#include "dbx_ptx.cuh"
+#include <mutex>
+
+namespace dbx {
+
+static constexpr int kThreads = 192;
+static constexpr int kMaxStages = 8;
+static constexpr int kSmemBudget = 220 * 1024;
+
+// ------------------------------------------------------------------------------------------------ host helpers
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  });
+  return fn;
+}
+
+int encode_act_map(CUtensorMap* m, const Act& a, const Tile& t) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return DBX_ERR_DRIVER;
+  if (a.cs % 8 || a.coff % 8 || a.C <= 0) return DBX_ERR_ARG;
+  cuuint64_t dims[4] = {(cuuint64_t)a.C, (cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)a.N};
+  cuuint64_t strides[3] = {(cuuint64_t)a.cs * 2, (cuuint64_t)a.W * a.cs * 2, (cuuint64_t)a.H * a.W * a.cs * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)t.tw, (cuuint32_t)t.th, (cuuint32_t)t.tn};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  void* base = (void*)((char*)a.ptr + (size_t)a.coff * 2);
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? DBX_OK : DBX_ERR_TMAP;
+}
+
+int encode_mat_map(CUtensorMap* m, const void* ptr, int rows, int cols, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return DBX_ERR_DRIVER;
+  if (cols % 8) return DBX_ERR_ARG;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)ptr, dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? DBX_OK : DBX_ERR_TMAP;
+}
+
+Tile choose_tile(int W, int H, int N, bool need_mult16) {
+  Tile best{};
+  double best_score = -1.0;
+  for (int tw = 1; tw <= 128 && tw <= W; ++tw) {
+    for (int th = 1; tw * th <= 128 && th <= H; ++th) {
+      for (int tn = 1; tw * th * tn <= 128 && tn <= N; ++tn) {
+        int rows = tw * th * tn;
+        if (need_mult16 && (rows % 16)) continue;
+        if (!need_mult16 && rows < 64 && (long)W * H * N >= 64) continue;
+        long tiles = (long)((W + tw - 1) / tw) * ((H + th - 1) / th) * ((N + tn - 1) / tn);
+        // fprop pays 128 MMA rows per tile whatever the box; wgrad pays the box rows (zero-filled K).
+        double denom = need_mult16 ? (double)tiles * rows : (double)tiles * 128.0;
+        double eff = (double)W * H * N / denom;
+        double halo = (double)(tw + 2) * (th + 2) / ((double)tw * th);
+        double score = eff + 1e-3 * (rows / 128.0) - 1e-4 * halo + 1e-6 * (tw / 128.0);
+        if (score > best_score) {
+          best_score = score;
+          best.tw = tw; best.th = th; best.tn = tn;
+          best.tiles_w = (W + tw - 1) / tw; best.tiles_h = (H + th - 1) / th; best.tiles_n = (N + tn - 1) / tn;
+        }
+      }
+    }
+  }
+  return best;
+}
+
+static uint32_t tmem_cols_for(int n) {
+  uint32_t c = 32;
+  while ((int)c < n) c <<= 1;
+  return c;
+}
+
+// ------------------------------------------------------------------------------------------------ fprop kernel
+struct FpropParams {
+  int tw, th, tn, tiles_w, tiles_h, tiles_n;
+  int out_W, out_H, out_N;
+  int R, S, pad;
+  int cin, cin_blocks;
+  int m_tiles, n_tiles, block_n;
+  int cout;
+  int stages;
+  uint32_t idesc, tmem_cols;
+  const float* bias;
+  int relu;
+  const bf16* aux;
+  int aux_cs, aux_coff, aux_mode;
+  void* out;
+  int out_cs, out_coff, out_fp32;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const FpropParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t full_bar[kMaxStages], empty_bar[kMaxStages], tfull_bar[2], tempty_bar[2];
+  __shared__ uint32_t tmem_base_s;
+
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t a_bytes = (uint32_t)(p.tw * p.th * p.tn) * 128u;
+  const uint32_t b_bytes = (uint32_t)p.block_n * 128u;
+  const uint32_t stage_bytes = 16384u + b_bytes;
+  const int total = p.m_tiles * p.n_tiles;
+  const int num_kb = p.R * p.S * p.cin_blocks;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc(&tmem_base_s, p.tmem_cols); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x) {
+        const int nt = t / p.m_tiles, mt = t % p.m_tiles;
+        const int w0 = (mt % p.tiles_w) * p.tw;
+        const int h0 = ((mt / p.tiles_w) % p.tiles_h) * p.th;
+        const int n0 = (mt / (p.tiles_w * p.tiles_h)) * p.tn;
+        for (int r = 0; r < p.R; ++r)
+          for (int s = 0; s < p.S; ++s)
+            for (int cb = 0; cb < p.cin_blocks; ++cb) {
+              mbar_wait(&empty_bar[stage], phase ^ 1);
+              uint8_t* sa = smem + (size_t)stage * stage_bytes;
+              mbar_arrive_expect_tx(&full_bar[stage], a_bytes + b_bytes);
+              tma_load_4d(&tmA, &full_bar[stage], sa, cb * 64, w0 + s - p.pad, h0 + r - p.pad, n0);
+              tma_load_2d(&tmB, &full_bar[stage], sa + 16384, (r * p.S + s) * p.cin + cb * 64, nt * p.block_n);
+              if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0; int it = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+        const int buf = it & 1; const uint32_t use = (uint32_t)(it >> 1);
+        mbar_wait(&tempty_bar[buf], (use & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem + (uint32_t)(buf * p.block_n);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + (size_t)stage * stage_bytes);
+          const uint32_t b_addr = a_addr + 16384u;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t da = umma_smem_desc_sw128(a_addr + k * 32, 16, 1024);
+            const uint64_t db = umma_smem_desc_sw128(b_addr + k * 32, 16, 1024);
+            umma_bf16(d_tmem, da, db, p.idesc, (uint32_t)((kb | k) != 0));
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull_bar[buf]);
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5 -> TMEM lane quarters 2,3,0,1) =====================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int box_rows = p.tw * p.th * p.tn;
+    int it = 0;
+    for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+      const int buf = it & 1; const uint32_t use = (uint32_t)(it >> 1);
+      const int nt = t / p.m_tiles, mt = t % p.m_tiles;
+      const int w = (mt % p.tiles_w) * p.tw + row % p.tw;
+      const int h = ((mt / p.tiles_w) % p.tiles_h) * p.th + (row / p.tw) % p.th;
+      const int n = (mt / (p.tiles_w * p.tiles_h)) * p.tn + row / (p.tw * p.th);
+      const bool valid = row < box_rows && w < p.out_W && h < p.out_H && n < p.out_N;
+      const size_t pix = ((size_t)n * p.out_H + h) * p.out_W + w;
+      mbar_wait(&tfull_bar[buf], use & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * p.block_n);
+      for (int c0 = 0; c0 < p.block_n; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld_x16(taddr + c0, v);
+        tmem_ld_wait();
+        const int ch = nt * p.block_n + c0;
+        if (valid && ch < p.cout) {
+          float f[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+          if (p.bias) {
+            const float4* bp = reinterpret_cast<const float4*>(p.bias + ch);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float4 b4 = __ldg(bp + j);
+              f[4 * j] += b4.x; f[4 * j + 1] += b4.y; f[4 * j + 2] += b4.z; f[4 * j + 3] += b4.w;
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+          }
+          if (p.aux_mode) {
+            const uint4* ap = reinterpret_cast<const uint4*>(p.aux + pix * p.aux_cs + p.aux_coff + ch);
+            uint4 a0 = __ldg(ap), a1 = __ldg(ap + 1);
+            uint32_t au[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float lo = bf16lo(au[j]), hi = bf16hi(au[j]);
+              if (p.aux_mode == 1) {
+                f[2 * j] = lo > 0.f ? f[2 * j] : 0.f;
+                f[2 * j + 1] = hi > 0.f ? f[2 * j + 1] : 0.f;
+              } else {
+                f[2 * j] *= lo;
+                f[2 * j + 1] *= hi;
+              }
+            }
+          }
+          if (p.out_fp32) {
+            float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + pix * p.out_cs + p.out_coff + ch);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+          } else {
+            uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + pix * p.out_cs + p.out_coff + ch);
+            op[0] = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
+                               pack_bf16x2(f[6], f[7]));
+            op[1] = make_uint4(pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]), pack_bf16x2(f[12], f[13]),
+                               pack_bf16x2(f[14], f[15]));
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem, p.tmem_cols); }
+}
+
+static int set_max_smem(const void* fn) {
+  cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget + 2048);
+  return (int)e;
+}
+
+int conv_fprop(const Act& x, const void* wk, int R, int S, int pad, const Act& out, const ConvEpilogue& epi,
+               int block_n, cudaStream_t stream) {
+  if (!x.ptr || !wk || !out.ptr) return DBX_ERR_ARG;
+  if (x.C % 64 || out.C % 16) return DBX_ERR_ARG;
+  if (out.H != x.H + 2 * pad - R + 1 || out.W != x.W + 2 * pad - S + 1 || out.N != x.N) return DBX_ERR_ARG;
+  const int out_align = epi.out_fp32 ? 4 : 8;
+  if (out.cs % out_align || out.coff % out_align) return DBX_ERR_ARG;
+  if (epi.aux_mode && (!epi.aux || epi.aux_cs % 8 || epi.aux_coff % 8)) return DBX_ERR_ARG;
+  if (block_n <= 0) block_n = out.C >= 256 ? 256 : out.C;
+  if (block_n % 16 || block_n > 256 || block_n < 16) return DBX_ERR_ARG;
+
+  Tile t = choose_tile(out.W, out.H, out.N, false);
+  CUtensorMap tmA, tmB;
+  int rc = encode_act_map(&tmA, x, t);
+  if (rc) return rc;
+  rc = encode_mat_map(&tmB, wk, out.C, R * S * x.C, block_n);
+  if (rc) return rc;
+
+  FpropParams p{};
+  p.tw = t.tw; p.th = t.th; p.tn = t.tn; p.tiles_w = t.tiles_w; p.tiles_h = t.tiles_h; p.tiles_n = t.tiles_n;
+  p.out_W = out.W; p.out_H = out.H; p.out_N = out.N;
+  p.R = R; p.S = S; p.pad = pad;
+  p.cin = x.C; p.cin_blocks = x.C / 64;
+  p.m_tiles = t.count(); p.n_tiles = (out.C + block_n - 1) / block_n; p.block_n = block_n;
+  p.cout = out.C;
+  const int stage_bytes = 16384 + block_n * 128;
+  p.stages = kSmemBudget / stage_bytes;
+  if (p.stages > kMaxStages) p.stages = kMaxStages;
+  if (p.stages < 2) return DBX_ERR_ARG;
+  p.idesc = umma_idesc_bf16(128, block_n, 0, 0);
+  p.tmem_cols = tmem_cols_for(2 * block_n);
+  p.bias = epi.bias; p.relu = epi.relu;
+  p.aux = (const bf16*)epi.aux; p.aux_cs = epi.aux_cs; p.aux_coff = epi.aux_coff; p.aux_mode = epi.aux_mode;
+  p.out = out.ptr; p.out_cs = out.cs; p.out_coff = out.coff; p.out_fp32 = epi.out_fp32;
+
+  static int attr_rc = set_max_smem((const void*)conv_fprop_kernel);
+  if (attr_rc) return attr_rc;
+  const int total = p.m_tiles * p.n_tiles;
+  const int grid = total < num_sms() ? total : num_sms();
+  const size_t smem = (size_t)p.stages * stage_bytes + 1024;
+  conv_fprop_kernel<<<grid, kThreads, smem, stream>>>(tmA, tmB, p);
+  return (int)cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------ wgrad kernel
+struct WgradParams {
+  int tw, th, tn, tiles_w, tiles_h, tiles_n;
+  int R, S, pad;
+  int kp;
+  int cin_blocks, q_total, nb, block_n;
+  int m_tiles, q_tiles, splits, boxes_total, boxes_per_split;
+  int cout, ldw;
+  float* dw;
+  int stages;
+  uint32_t idesc, tmem_cols;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ CUtensorMap tmX,
+                  const WgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t full_bar[kMaxStages], empty_bar[kMaxStages], tfull_bar[2], tempty_bar[2];
+  __shared__ uint32_t tmem_base_s;
+
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t box_bytes = (uint32_t)p.kp * 128u;           // one [kp pixels][64 ch] tile
+  const uint32_t stage_bytes = box_bytes * (2u + (uint32_t)p.nb);
+  const int tiles_per_split = p.m_tiles * p.q_tiles;
+  const int total = tiles_per_split * p.splits;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmDy);
+    tma_prefetch_desc(&tmX);
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc(&tmem_base_s, p.tmem_cols); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x) {
+        const int split = t / tiles_per_split, rem = t % tiles_per_split;
+        const int m = rem / p.q_tiles, q0 = (rem % p.q_tiles) * p.nb;
+        int nvalid = p.q_total - q0; if (nvalid > p.nb) nvalid = p.nb;
+        const int b_begin = split * p.boxes_per_split;
+        int b_end = b_begin + p.boxes_per_split; if (b_end > p.boxes_total) b_end = p.boxes_total;
+        for (int b = b_begin; b < b_end; ++b) {
+          const int w0 = (b % p.tiles_w) * p.tw;
+          const int h0 = ((b / p.tiles_w) % p.tiles_h) * p.th;
+          const int n0 = (b / (p.tiles_w * p.tiles_h)) * p.tn;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + (size_t)stage * stage_bytes;
+          mbar_arrive_expect_tx(&full_bar[stage], box_bytes * (2u + (uint32_t)nvalid));
+          tma_load_4d(&tmDy, &full_bar[stage], sa, m * 128, w0, h0, n0);
+          tma_load_4d(&tmDy, &full_bar[stage], sa + box_bytes, m * 128 + 64, w0, h0, n0);
+          for (int j = 0; j < nvalid; ++j) {
+            const int qq = q0 + j, tap = qq / p.cin_blocks, cb = qq % p.cin_blocks;
+            const int r = tap / p.S, s = tap % p.S;
+            tma_load_4d(&tmX, &full_bar[stage], sa + box_bytes * (2u + j), cb * 64, w0 + s - p.pad, h0 + r - p.pad, n0);
+          }
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0; int it = 0;
+      const int ksteps = p.kp / 16;
+      for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+        const int buf = it & 1; const uint32_t use = (uint32_t)(it >> 1);
+        const int split = t / tiles_per_split;
+        const int b_begin = split * p.boxes_per_split;
+        int b_end = b_begin + p.boxes_per_split; if (b_end > p.boxes_total) b_end = p.boxes_total;
+        mbar_wait(&tempty_bar[buf], (use & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem + (uint32_t)(buf * p.block_n);
+        for (int b = b_begin; b < b_end; ++b) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + (size_t)stage * stage_bytes);
+          const uint32_t b_addr = a_addr + 2u * box_bytes;
+          for (int ks = 0; ks < ksteps; ++ks) {
+            // MN-major SW128: 64-channel atoms LBO apart, groups of 8 pixel rows SBO = 1024 B apart.
+            const uint64_t da = umma_smem_desc_sw128(a_addr + ks * 2048, box_bytes, 1024);
+            const uint64_t db = umma_smem_desc_sw128(b_addr + ks * 2048, box_bytes, 1024);
+            umma_bf16(d_tmem, da, db, p.idesc, (uint32_t)((b > b_begin) | (ks != 0)));
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull_bar[buf]);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    int it = 0;
+    for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+      const int buf = it & 1; const uint32_t use = (uint32_t)(it >> 1);
+      const int rem = t % tiles_per_split;
+      const int m = rem / p.q_tiles, q0 = (rem % p.q_tiles) * p.nb;
+      const int row = m * 128 + q * 32 + lane;
+      const bool valid = row < p.cout;
+      mbar_wait(&tfull_bar[buf], use & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * p.block_n);
+      float* drow = p.dw + (size_t)row * p.ldw + (size_t)q0 * 64;
+      for (int c0 = 0; c0 < p.block_n; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld_x16(taddr + c0, v);
+        tmem_ld_wait();
+        if (valid && (q0 + c0 / 64) < p.q_total) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            red_add_v4(drow + c0 + 4 * j, __uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                       __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem, p.tmem_cols); }
+}
+
+int conv_wgrad(const Act& x, const Act& dy, int R, int S, int pad, float* dw, int block_n, cudaStream_t stream) {
+  if (!x.ptr || !dy.ptr || !dw) return DBX_ERR_ARG;
+  if (x.C % 64 || dy.C % 16) return DBX_ERR_ARG;
+  if (dy.H != x.H + 2 * pad - R + 1 || dy.W != x.W + 2 * pad - S + 1 || dy.N != x.N) return DBX_ERR_ARG;
+  const int q_total = R * S * (x.C / 64);
+  if (block_n <= 0) {
+    block_n = 256;
+    if (q_total * 64 < block_n) block_n = q_total * 64;
+    // small layers: prefer a column split that leaves no ragged tail (e.g. 9 taps x 64 ch -> 3 x 192)
+    if (q_total % 4 && q_total % 3 == 0 && q_total >= 3) block_n = 192;
+  }
+  if (block_n % 64 || block_n > 256 || block_n < 64) return DBX_ERR_ARG;
+
+  Tile t = choose_tile(dy.W, dy.H, dy.N, true);
+  CUtensorMap tmDy, tmX;
+  int rc = encode_act_map(&tmDy, dy, t);
+  if (rc) return rc;
+  rc = encode_act_map(&tmX, x, t);
+  if (rc) return rc;
+
+  WgradParams p{};
+  p.tw = t.tw; p.th = t.th; p.tn = t.tn; p.tiles_w = t.tiles_w; p.tiles_h = t.tiles_h; p.tiles_n = t.tiles_n;
+  p.R = R; p.S = S; p.pad = pad;
+  p.kp = t.rows();
+  p.cin_blocks = x.C / 64; p.q_total = q_total; p.nb = block_n / 64; p.block_n = block_n;
+  p.m_tiles = (dy.C + 127) / 128; p.q_tiles = (q_total + p.nb - 1) / p.nb;
+  p.boxes_total = t.count();
+  const int tiles = p.m_tiles * p.q_tiles;
+  int splits = num_sms() / tiles;
+  if (splits < 1) splits = 1;
+  if (splits > p.boxes_total) splits = p.boxes_total;
+  p.boxes_per_split = (p.boxes_total + splits - 1) / splits;
+  p.splits = (p.boxes_total + p.boxes_per_split - 1) / p.boxes_per_split;
+  p.cout = dy.C; p.ldw = R * S * x.C; p.dw = dw;
+  const int stage_bytes = p.kp * 128 * (2 + p.nb);
+  p.stages = kSmemBudget / stage_bytes;
+  if (p.stages > kMaxStages) p.stages = kMaxStages;
+  if (p.stages < 2) return DBX_ERR_ARG;
+  p.idesc = umma_idesc_bf16(128, block_n, 1, 1);
+  p.tmem_cols = tmem_cols_for(2 * block_n);
+
+  static int attr_rc = set_max_smem((const void*)conv_wgrad_kernel);
+  if (attr_rc) return attr_rc;
+  const int total = tiles * p.splits;
+  const int grid = total < num_sms() ? total : num_sms();
+  const size_t smem = (size_t)p.stages * stage_bytes + 1024;
+  conv_wgrad_kernel<<<grid, kThreads, smem, stream>>>(tmDy, tmX, p);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace dbx
