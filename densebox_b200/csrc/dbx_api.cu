@@ -45,4 +45,33 @@ int dbx_conv_wgrad(const void* x, int N, int H, int W, int cin, int x_cs, int x_
   return conv_wgrad(ax, ad, R, S, pad, dw, block_n, (cudaStream_t)stream);
 }
 
+int dbx_loss_fwd_bwd(const float* head, int HC, const float* rf, int RC, const float* bbox, const float* vertices,
+                     const float* labels, const long long* rand_idx, int rand_stride, const long long* lm_rand_idx,
+                     int variant, float lambda_loc, float lambda_det, float lambda_lm, int global_pos,
+                     int global_batch, const int* global_pos_ptr, int clamp_lm, int B, void* scratch, float* loss,
+                     int* info, void* d_head_bf16, void* d_rf_bf16, float* d_head_f32, float* d_rf_f32,
+                     unsigned char* mask_out, unsigned char* lm_mask_out, void* stream) {
+  if (!scratch) return DBX_ERR_ARG;
+  LossParams p{};
+  p.head = head; p.HC = HC; p.rf = rf; p.RC = RC; p.bbox = bbox; p.vertices = vertices; p.labels = labels;
+  p.rand_idx = rand_idx; p.rand_stride = rand_stride; p.lm_rand_idx = lm_rand_idx; p.variant = variant;
+  p.lambda_loc = lambda_loc; p.lambda_det = lambda_det; p.lambda_lm = lambda_lm;
+  p.global_pos = global_pos; p.global_batch = global_batch; p.global_pos_ptr = global_pos_ptr;
+  p.clamp_lm = clamp_lm; p.B = B;
+  p.counter = (unsigned int*)scratch; p.loss_partial = (float*)scratch + 4;
+  p.loss = loss; p.info = info;
+  p.d_head = (__nv_bfloat16*)d_head_bf16; p.d_rf = (__nv_bfloat16*)d_rf_bf16;
+  p.d_head_f32 = d_head_f32; p.d_rf_f32 = d_rf_f32; p.mask_out = mask_out; p.lm_mask_out = lm_mask_out;
+  return loss_fwd_bwd(p, (cudaStream_t)stream);
+}
+
+int dbx_count_positives(const float* bbox, const float* labels, int B, int* out, void* stream) {
+  return count_positives(bbox, labels, B, out, (cudaStream_t)stream);
+}
+
+int dbx_dropout_mask(void* mask, unsigned long long n, unsigned long long seed, unsigned long long offset,
+                     void* stream) {
+  return dropout_mask(mask, (size_t)n, seed, offset, (cudaStream_t)stream);
+}
+
 }  // extern "C"

@@ -62,4 +62,55 @@ int conv_fprop(const Act& x, const void* wk, int R, int S, int pad, const Act& o
 // dw has row stride R*S*x.C; rows = dy.C.
 int conv_wgrad(const Act& x, const Act& dy, int R, int S, int pad, float* dw, int block_n, cudaStream_t stream);
 
+
+// ---- HBM-bound kernels (dbx_elementwise.cu)
+int im2col3x3_c3(const float* x, void* out, int N, int H, int W, cudaStream_t st);
+int maxpool2x2_fwd(const Act& y, const Act& o, cudaStream_t st);
+int maxpool2x2_bwd(const Act& y, const Act& dp, const Act* add, const Act& dy, cudaStream_t st);
+int upsample_bilinear_fwd(const Act& in, const Act& out, cudaStream_t st);
+int upsample_bilinear_bwd(const Act& dout, const Act* relu_y, const Act& din, cudaStream_t st);
+int colsum(const Act& dy, float* db, cudaStream_t st);
+int pack_weights(const float* src, int co, int ci, int R, int S, long s_co, long s_ci, long s_r, long s_s, void* dstK,
+                 long ldK, long rowK, long kK, int cin_pad, void* dstD, long ldD, long rowD, long kD, int cout_pad,
+                 float* dstF, cudaStream_t st);
+int unpack_weights(const float* srcK, long ldK, long rowK, long kK, int cin_pad, float* dst, int co, int ci, int R,
+                   int S, long s_co, long s_ci, long s_r, long s_s, cudaStream_t st);
+int transpose_dgrad(const void* wk, void* wd, int rows, int T, int cin_pad, int kpad, cudaStream_t st);
+int sgd_step(float* w, float* g, float* v, void* wb, size_t n, float lr, float momentum, float wd, int first,
+             int zero_grad, cudaStream_t st);
+int cast_bf16(const float* src, void* dst, size_t n, cudaStream_t st);
+int blockdiag_mask(float* g, int rows, int ld, int nh, const int* start, cudaStream_t st);
+int dropout_mask(void* mask, size_t n, unsigned long long seed, unsigned long long offset, cudaStream_t st);
+int refine_pool_pack(const float* head, int HC, void* pooled, int N, int H, int W, cudaStream_t st);
+int refine_pool_bwd(const float* head, int HC, const void* dpooled, void* dhead, int N, int H, int W, cudaStream_t st);
+
+// ---- fused loss (dbx_loss.cu)
+struct LossParams {
+  const float* head; int HC;      // [B,60,60,HC] fp32: ch0 score, 1..4 loc, 5..8 landmark heat, 9..16 landmark loc
+  const float* rf; int RC;        // [B,60,60,RC] fp32, ch0 = refine score (variants 1,2)
+  const float* bbox;              // [B,4] 60-space
+  const float* vertices;          // [B,8] or null
+  const float* labels;            // [B] or null (= all positive patches)
+  const long long* rand_idx; int rand_stride;  // [B,rand_stride] injected random negatives (first `half` used)
+  const long long* lm_rand_idx;   // [B,4]
+  int variant;                    // 0 DenseBox, 1 DenseBoxLM, 2 DenseBoxLMLOC
+  float lambda_loc, lambda_det, lambda_lm;
+  int global_pos, global_batch;   // data-parallel: batch-global positive count / batch size; <0 = use this launch
+  const int* global_pos_ptr;      // optional device int: overrides global_pos (filled by count_positives + allreduce)
+  int clamp_lm;                   // init_lm_heatmap_pn clamping (:1899-1907)
+  int B;
+  float* loss_partial;            // [B]
+  float* loss;                    // [1]
+  unsigned int* counter;          // zero before first use; self-resetting
+  __nv_bfloat16* d_head;          // [B,60,60,64] bf16 or null
+  __nv_bfloat16* d_rf;            // [B,60,60,64] bf16 or null
+  float* d_head_f32;              // [B,60,60,HC] or null
+  float* d_rf_f32;                // [B,60,60,RC] or null
+  unsigned char* mask_out;        // [B,3600] or null
+  unsigned char* lm_mask_out;     // [B,4,3600] or null
+  int* info;                      // [2] = {half, pos} or null
+};
+int loss_fwd_bwd(const LossParams& p, cudaStream_t st);
+int count_positives(const float* bbox, const float* labels, int B, int* out, cudaStream_t st);
+
 }  // namespace dbx

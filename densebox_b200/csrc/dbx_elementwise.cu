@@ -1,0 +1,513 @@
+// densebox_b200 — HBM-bound kernels around the tensor-core convolutions: input ingest (im2col for the 3-channel
+// first layer), 2x2 max-pool forward / backward(+ReLU mask), bilinear(align_corners) upsample forward / backward
+// (the upsample half of DenseBox.py:213-219; the concat half is free — conv3_4 writes straight into the fusion
+// buffer), bias gradients, weight re-layout, dropout masks, refine-branch glue and the fused SGD step.
+// All kernels move 16-byte (8 x bf16) vectors, one vector per thread, channel-fastest so that warps are coalesced.
+#include "dbx_common.h"
+#include "dbx_ptx.cuh"
+
+namespace dbx {
+
+static inline int grid_for(size_t work, int block) { return (int)((work + block - 1) / block); }
+
+__device__ __forceinline__ uint4 ldg16(const bf16* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+__device__ __forceinline__ void unpack8(const uint4& u, float* f) {
+  f[0] = bf16lo(u.x); f[1] = bf16hi(u.x); f[2] = bf16lo(u.y); f[3] = bf16hi(u.y);
+  f[4] = bf16lo(u.z); f[5] = bf16hi(u.z); f[6] = bf16lo(u.w); f[7] = bf16hi(u.w);
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+}
+__device__ __forceinline__ bf16* at(const Act& a, int n, int y, int x, int c) {
+  return reinterpret_cast<bf16*>(a.ptr) + (((size_t)n * a.H + y) * a.W + x) * a.cs + a.coff + c;
+}
+
+// ------------------------------------------------------------------------------------------------ ingest
+// X fp32 NCHW [N,3,H,W] -> bf16 [N,H,W,64]: channel (r*3+s)*3+c holds X[n,c,y+r-1,x+s-1] (zero outside), channels
+// 27..63 are zero.  conv1_1 (DenseBox.py:185) then is a K=64 1x1 GEMM on the tensor cores.
+__global__ void im2col3x3_c3_kernel(const float* __restrict__ x, bf16* __restrict__ out, int N, int H, int W) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = (size_t)N * H * W * 8;
+  if (idx >= total) return;
+  const int chunk = (int)(idx & 7);
+  const size_t pix = idx >> 3;
+  const int xw = (int)(pix % W), y = (int)((pix / W) % H), n = (int)(pix / ((size_t)W * H));
+  float f[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int k = chunk * 8 + j;
+    float v = 0.f;
+    if (k < 27) {
+      const int tap = k / 3, c = k - tap * 3, r = tap / 3, s = tap - r * 3;
+      const int yy = y + r - 1, xx = xw + s - 1;
+      if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = __ldg(x + (((size_t)n * 3 + c) * H + yy) * W + xx);
+    }
+    f[j] = v;
+  }
+  reinterpret_cast<uint4*>(out)[idx] = pack8(f);
+}
+
+int im2col3x3_c3(const float* x, void* out, int N, int H, int W, cudaStream_t st) {
+  if (!x || !out) return DBX_ERR_ARG;
+  const size_t total = (size_t)N * H * W * 8;
+  im2col3x3_c3_kernel<<<grid_for(total, 256), 256, 0, st>>>(x, (bf16*)out, N, H, W);
+  return (int)cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------ max-pool 2x2
+__global__ void maxpool2x2_fwd_kernel(Act y, Act o) {
+  const int cc = o.C / 8;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = (size_t)o.N * o.H * o.W * cc;
+  if (idx >= total) return;
+  const int c = (int)(idx % cc) * 8;
+  const size_t pix = idx / cc;
+  const int ox = (int)(pix % o.W), oy = (int)((pix / o.W) % o.H), n = (int)(pix / ((size_t)o.W * o.H));
+  float a[8], b[8];
+  unpack8(ldg16(at(y, n, 2 * oy, 2 * ox, c)), a);
+  unpack8(ldg16(at(y, n, 2 * oy, 2 * ox + 1, c)), b);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a[j] = fmaxf(a[j], b[j]);
+  unpack8(ldg16(at(y, n, 2 * oy + 1, 2 * ox, c)), b);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a[j] = fmaxf(a[j], b[j]);
+  unpack8(ldg16(at(y, n, 2 * oy + 1, 2 * ox + 1, c)), b);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a[j] = fmaxf(a[j], b[j]);
+  *reinterpret_cast<uint4*>(at(o, n, oy, ox, c)) = pack8(a);
+}
+
+int maxpool2x2_fwd(const Act& y, const Act& o, cudaStream_t st) {
+  if (y.H != 2 * o.H || y.W != 2 * o.W || y.C != o.C || y.N != o.N || y.C % 8) return DBX_ERR_ARG;
+  const size_t total = (size_t)o.N * o.H * o.W * (o.C / 8);
+  maxpool2x2_fwd_kernel<<<grid_for(total, 256), 256, 0, st>>>(y, o);
+  return (int)cudaGetLastError();
+}
+
+// dy = relu'(y) * ( maxpool_bwd(dp)  [+ add] ): gradient goes to the FIRST maximum of each window in scan order
+// (torch max_pool2d semantics), then the ReLU mask of the producing conv (y > 0) is applied.
+__global__ void maxpool2x2_bwd_kernel(Act y, Act dp, Act add, int has_add, Act dy) {
+  const int cc = dp.C / 8;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = (size_t)dp.N * dp.H * dp.W * cc;
+  if (idx >= total) return;
+  const int c = (int)(idx % cc) * 8;
+  const size_t pix = idx / cc;
+  const int ox = (int)(pix % dp.W), oy = (int)((pix / dp.W) % dp.H), n = (int)(pix / ((size_t)dp.W * dp.H));
+  float v[4][8], g[8], o[4][8];
+  unpack8(ldg16(at(y, n, 2 * oy, 2 * ox, c)), v[0]);
+  unpack8(ldg16(at(y, n, 2 * oy, 2 * ox + 1, c)), v[1]);
+  unpack8(ldg16(at(y, n, 2 * oy + 1, 2 * ox, c)), v[2]);
+  unpack8(ldg16(at(y, n, 2 * oy + 1, 2 * ox + 1, c)), v[3]);
+  unpack8(ldg16(at(dp, n, oy, ox, c)), g);
+  if (has_add) {
+    unpack8(ldg16(at(add, n, 2 * oy, 2 * ox, c)), o[0]);
+    unpack8(ldg16(at(add, n, 2 * oy, 2 * ox + 1, c)), o[1]);
+    unpack8(ldg16(at(add, n, 2 * oy + 1, 2 * ox, c)), o[2]);
+    unpack8(ldg16(at(add, n, 2 * oy + 1, 2 * ox + 1, c)), o[3]);
+  } else {
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[k][j] = 0.f;
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    int arg = 0; float m = v[0][j];
+    if (v[1][j] > m) { m = v[1][j]; arg = 1; }
+    if (v[2][j] > m) { m = v[2][j]; arg = 2; }
+    if (v[3][j] > m) { m = v[3][j]; arg = 3; }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float r = o[k][j] + (k == arg ? g[j] : 0.f);
+      o[k][j] = v[k][j] > 0.f ? r : 0.f;
+    }
+  }
+  *reinterpret_cast<uint4*>(at(dy, n, 2 * oy, 2 * ox, c)) = pack8(o[0]);
+  *reinterpret_cast<uint4*>(at(dy, n, 2 * oy, 2 * ox + 1, c)) = pack8(o[1]);
+  *reinterpret_cast<uint4*>(at(dy, n, 2 * oy + 1, 2 * ox, c)) = pack8(o[2]);
+  *reinterpret_cast<uint4*>(at(dy, n, 2 * oy + 1, 2 * ox + 1, c)) = pack8(o[3]);
+}
+
+int maxpool2x2_bwd(const Act& y, const Act& dp, const Act* add, const Act& dy, cudaStream_t st) {
+  if (y.H != 2 * dp.H || y.W != 2 * dp.W || y.C != dp.C || dy.C != y.C || dy.H != y.H || dy.W != y.W || y.C % 8)
+    return DBX_ERR_ARG;
+  const size_t total = (size_t)dp.N * dp.H * dp.W * (dp.C / 8);
+  maxpool2x2_bwd_kernel<<<grid_for(total, 256), 256, 0, st>>>(y, dp, add ? *add : y, add ? 1 : 0, dy);
+  return (int)cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------ bilinear upsample
+// nn.Upsample(size, mode='bilinear', align_corners=True) (DenseBox.py:213-216, :468-470): src = dst*(in-1)/(out-1),
+// float arithmetic identical to ATen's area_pixel_compute_source_index / linear weights.
+struct Lin { int i0, i1; float l0, l1; };
+__device__ __forceinline__ Lin lin_coord(int d, float scale, int in_size) {
+  Lin r;
+  const float src = scale * (float)d;
+  r.i0 = (int)src;
+  r.i1 = r.i0 + (r.i0 < in_size - 1 ? 1 : 0);
+  r.l1 = src - (float)r.i0;
+  r.l0 = 1.f - r.l1;
+  return r;
+}
+
+__global__ void upsample_fwd_kernel(Act in, Act out, float sh, float sw) {
+  const int cc = out.C / 8;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = (size_t)out.N * out.H * out.W * cc;
+  if (idx >= total) return;
+  const int c = (int)(idx % cc) * 8;
+  const size_t pix = idx / cc;
+  const int ox = (int)(pix % out.W), oy = (int)((pix / out.W) % out.H), n = (int)(pix / ((size_t)out.W * out.H));
+  const Lin ly = lin_coord(oy, sh, in.H), lx = lin_coord(ox, sw, in.W);
+  float a[8], b[8], c0[8], d[8], o[8];
+  unpack8(ldg16(at(in, n, ly.i0, lx.i0, c)), a);
+  unpack8(ldg16(at(in, n, ly.i0, lx.i1, c)), b);
+  unpack8(ldg16(at(in, n, ly.i1, lx.i0, c)), c0);
+  unpack8(ldg16(at(in, n, ly.i1, lx.i1, c)), d);
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    o[j] = ly.l0 * (lx.l0 * a[j] + lx.l1 * b[j]) + ly.l1 * (lx.l0 * c0[j] + lx.l1 * d[j]);
+  *reinterpret_cast<uint4*>(at(out, n, oy, ox, c)) = pack8(o);
+}
+
+int upsample_bilinear_fwd(const Act& in, const Act& out, cudaStream_t st) {
+  if (in.C != out.C || in.N != out.N || in.C % 8) return DBX_ERR_ARG;
+  const float sh = out.H > 1 ? (float)(in.H - 1) / (float)(out.H - 1) : 0.f;
+  const float sw = out.W > 1 ? (float)(in.W - 1) / (float)(out.W - 1) : 0.f;
+  const size_t total = (size_t)out.N * out.H * out.W * (out.C / 8);
+  upsample_fwd_kernel<<<grid_for(total, 256), 256, 0, st>>>(in, out, sh, sw);
+  return (int)cudaGetLastError();
+}
+
+// din[n,iy,ix,:] = relu'(y) * sum over output pixels of their bilinear weight on (iy,ix) — a gather, so no atomics.
+__global__ void upsample_bwd_kernel(Act dout, Act y, int has_mask, Act din, float sh, float sw) {
+  const int cc = din.C / 8;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = (size_t)din.N * din.H * din.W * cc;
+  if (idx >= total) return;
+  const int c = (int)(idx % cc) * 8;
+  const size_t pix = idx / cc;
+  const int ix = (int)(pix % din.W), iy = (int)((pix / din.W) % din.H), n = (int)(pix / ((size_t)din.W * din.H));
+  int ylo = 0, yhi = dout.H - 1, xlo = 0, xhi = dout.W - 1;
+  if (sh > 0.f) { ylo = max(0, (int)floorf((iy - 1) / sh) - 1); yhi = min(dout.H - 1, (int)ceilf((iy + 1) / sh) + 1); }
+  if (sw > 0.f) { xlo = max(0, (int)floorf((ix - 1) / sw) - 1); xhi = min(dout.W - 1, (int)ceilf((ix + 1) / sw) + 1); }
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  for (int oy = ylo; oy <= yhi; ++oy) {
+    const Lin ly = lin_coord(oy, sh, din.H);
+    const float wy = (ly.i0 == iy ? ly.l0 : 0.f) + (ly.i1 == iy ? ly.l1 : 0.f);
+    if (wy == 0.f) continue;
+    for (int ox = xlo; ox <= xhi; ++ox) {
+      const Lin lx = lin_coord(ox, sw, din.W);
+      const float wx = (lx.i0 == ix ? lx.l0 : 0.f) + (lx.i1 == ix ? lx.l1 : 0.f);
+      if (wx == 0.f) continue;
+      float g[8];
+      unpack8(ldg16(at(dout, n, oy, ox, c)), g);
+      const float w = wy * wx;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += w * g[j];
+    }
+  }
+  if (has_mask) {
+    float m[8];
+    unpack8(ldg16(at(y, n, iy, ix, c)), m);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = m[j] > 0.f ? acc[j] : 0.f;
+  }
+  *reinterpret_cast<uint4*>(at(din, n, iy, ix, c)) = pack8(acc);
+}
+
+int upsample_bilinear_bwd(const Act& dout, const Act* relu_y, const Act& din, cudaStream_t st) {
+  if (din.C != dout.C || din.N != dout.N || din.C % 8) return DBX_ERR_ARG;
+  const float sh = dout.H > 1 ? (float)(din.H - 1) / (float)(dout.H - 1) : 0.f;
+  const float sw = dout.W > 1 ? (float)(din.W - 1) / (float)(dout.W - 1) : 0.f;
+  const size_t total = (size_t)din.N * din.H * din.W * (din.C / 8);
+  upsample_bwd_kernel<<<grid_for(total, 256), 256, 0, st>>>(dout, relu_y ? *relu_y : din, relu_y ? 1 : 0, din, sh, sw);
+  return (int)cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------ bias gradient
+// db[c] += sum over pixels of dy[pixel][c].  blockDim = (C/8) * rows; thread (r, chunk) keeps 8 fp32 partials.
+__global__ void colsum_kernel(Act dy, float* __restrict__ db, int rows, size_t pixels, size_t pix_per_block) {
+  extern __shared__ float red[];  // [rows][C]
+  const int cc = dy.C / 8;
+  const int chunk = threadIdx.x % cc, r = threadIdx.x / cc;
+  const size_t p0 = (size_t)blockIdx.x * pix_per_block;
+  size_t p1 = p0 + pix_per_block; if (p1 > pixels) p1 = pixels;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  const bf16* base = reinterpret_cast<const bf16*>(dy.ptr) + dy.coff + chunk * 8;
+  for (size_t p = p0 + r; p < p1; p += rows) {
+    float f[8];
+    unpack8(ldg16(base + p * dy.cs), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] += f[j];
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[(size_t)r * dy.C + chunk * 8 + j] = acc[j];
+  __syncthreads();
+  for (int c = threadIdx.x; c < dy.C; c += blockDim.x) {
+    float s = 0.f;
+    for (int k = 0; k < rows; ++k) s += red[(size_t)k * dy.C + c];
+    atomicAdd(db + c, s);
+  }
+}
+
+int colsum(const Act& dy, float* db, cudaStream_t st) {
+  if (!db || dy.C % 8 || dy.C > 2048) return DBX_ERR_ARG;
+  const int cc = dy.C / 8;
+  int rows = 256 / cc; if (rows < 1) rows = 1;
+  const size_t pixels = (size_t)dy.N * dy.H * dy.W;
+  int blocks = 4 * num_sms();
+  if ((size_t)blocks * rows > pixels) blocks = (int)((pixels + rows - 1) / rows);
+  if (blocks < 1) blocks = 1;
+  const size_t ppb = (pixels + blocks - 1) / blocks;
+  colsum_kernel<<<blocks, cc * rows, (size_t)rows * dy.C * sizeof(float), st>>>(dy, db, rows, pixels, ppb);
+  return (int)cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------ weights
+// Generic strided fp32 [co,ci,R,S] -> bf16 K-major  dstK[(rowK+o)*ldK + kK + (r*S+s)*cin_pad + i]
+//                                 and bf16 dgrad    dstD[(rowD+i)*ldD + kD + ((R-1-r)*S+(S-1-s))*cout_pad + o]
+__global__ void pack_weights_kernel(const float* __restrict__ src, int co, int ci, int R, int S, long s_co, long s_ci,
+                                    long s_r, long s_s, bf16* dstK, long ldK, long rowK, long kK, int cin_pad,
+                                    bf16* dstD, long ldD, long rowD, long kD, int cout_pad, float* dstF) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = (size_t)co * ci * R * S;
+  if (idx >= total) return;
+  const int i = (int)(idx % ci);
+  const int s = (int)((idx / ci) % S);
+  const int r = (int)((idx / ((size_t)ci * S)) % R);
+  const int o = (int)(idx / ((size_t)ci * S * R));
+  const float v = src[o * s_co + i * s_ci + r * s_r + s * s_s];
+  const bf16 b = __float2bfloat16_rn(v);
+  const size_t k_idx = (size_t)(rowK + o) * ldK + kK + (size_t)(r * S + s) * cin_pad + i;
+  if (dstK) dstK[k_idx] = b;
+  if (dstF) dstF[k_idx] = v;  // fp32 master in the same K-major layout
+  if (dstD) dstD[(size_t)(rowD + i) * ldD + kD + (size_t)((R - 1 - r) * S + (S - 1 - s)) * cout_pad + o] = b;
+}
+
+int pack_weights(const float* src, int co, int ci, int R, int S, long s_co, long s_ci, long s_r, long s_s, void* dstK,
+                 long ldK, long rowK, long kK, int cin_pad, void* dstD, long ldD, long rowD, long kD, int cout_pad,
+                 float* dstF, cudaStream_t st) {
+  if (!src) return DBX_ERR_ARG;
+  const size_t total = (size_t)co * ci * R * S;
+  pack_weights_kernel<<<grid_for(total, 256), 256, 0, st>>>(src, co, ci, R, S, s_co, s_ci, s_r, s_s, (bf16*)dstK, ldK,
+                                                            rowK, kK, cin_pad, (bf16*)dstD, ldD, rowD, kD, cout_pad,
+                                                            dstF);
+  return (int)cudaGetLastError();
+}
+
+// Inverse of the K-major packing for fp32 tensors (gradients / masters back to the torch [co,ci,R,S] layout).
+__global__ void unpack_weights_kernel(const float* __restrict__ srcK, long ldK, long rowK, long kK, int cin_pad,
+                                      float* __restrict__ dst, int co, int ci, int R, int S, long s_co, long s_ci,
+                                      long s_r, long s_s) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = (size_t)co * ci * R * S;
+  if (idx >= total) return;
+  const int i = (int)(idx % ci);
+  const int s = (int)((idx / ci) % S);
+  const int r = (int)((idx / ((size_t)ci * S)) % R);
+  const int o = (int)(idx / ((size_t)ci * S * R));
+  dst[o * s_co + i * s_ci + r * s_r + s * s_s] = srcK[(size_t)(rowK + o) * ldK + kK + (size_t)(r * S + s) * cin_pad + i];
+}
+
+int unpack_weights(const float* srcK, long ldK, long rowK, long kK, int cin_pad, float* dst, int co, int ci, int R,
+                   int S, long s_co, long s_ci, long s_r, long s_s, cudaStream_t st) {
+  if (!srcK || !dst) return DBX_ERR_ARG;
+  const size_t total = (size_t)co * ci * R * S;
+  unpack_weights_kernel<<<grid_for(total, 256), 256, 0, st>>>(srcK, ldK, rowK, kK, cin_pad, dst, co, ci, R, S, s_co,
+                                                              s_ci, s_r, s_s);
+  return (int)cudaGetLastError();
+}
+
+// bf16 K-major [rows][T][cin_pad] -> bf16 dgrad layout [cin_pad][T flipped][kpad >= rows] (32x32 smem tile
+// transpose; columns rows..kpad-1 stay zero from initialisation).
+__global__ void transpose_dgrad_kernel(const bf16* __restrict__ wk, bf16* __restrict__ wd, int rows, int T,
+                                       int cin_pad, int kpad) {
+  __shared__ bf16 tile[32][34];
+  const int t = blockIdx.z;
+  const int o0 = blockIdx.y * 32, i0 = blockIdx.x * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+  for (int k = ty; k < 32; k += 8) {
+    const int o = o0 + k, i = i0 + tx;
+    tile[k][tx] = (o < rows && i < cin_pad) ? wk[((size_t)o * T + t) * cin_pad + i] : __float2bfloat16_rn(0.f);
+  }
+  __syncthreads();
+  const int tf = T - 1 - t;  // (R-1-r)*S + (S-1-s) == T-1-(r*S+s)
+  for (int k = ty; k < 32; k += 8) {
+    const int i = i0 + k, o = o0 + tx;
+    if (i < cin_pad && o < rows) wd[((size_t)i * T + tf) * kpad + o] = tile[tx][k];
+  }
+}
+
+int transpose_dgrad(const void* wk, void* wd, int rows, int T, int cin_pad, int kpad, cudaStream_t st) {
+  if (!wk || !wd) return DBX_ERR_ARG;
+  dim3 grid((cin_pad + 31) / 32, (rows + 31) / 32, T), block(32, 8);
+  transpose_dgrad_kernel<<<grid, block, 0, st>>>((const bf16*)wk, (bf16*)wd, rows, T, cin_pad, kpad);
+  return (int)cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------ SGD
+// torch.optim.SGD(momentum, weight_decay, dampening=0, nesterov=False) (DenseBox.py:2821-2824, :2926) on the flat
+// fp32 master buffer; also refreshes the bf16 copy the tensor cores read and clears the gradient for the next step.
+__global__ void sgd_step_kernel(float* __restrict__ w, float* __restrict__ g, float* __restrict__ v,
+                                bf16* __restrict__ wb, size_t n, float lr, float momentum, float wd, int first,
+                                int zero_grad) {
+  const size_t i4 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i4 >= n) return;
+  float4 W = *reinterpret_cast<float4*>(w + i4), G = *reinterpret_cast<float4*>(g + i4);
+  float4 V = first ? make_float4(0.f, 0.f, 0.f, 0.f) : *reinterpret_cast<float4*>(v + i4);
+  float wv[4] = {W.x, W.y, W.z, W.w}, gv[4] = {G.x, G.y, G.z, G.w}, vv[4] = {V.x, V.y, V.z, V.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float d = gv[j] + wd * wv[j];
+    vv[j] = first ? d : momentum * vv[j] + d;
+    wv[j] = wv[j] - lr * vv[j];
+  }
+  *reinterpret_cast<float4*>(w + i4) = make_float4(wv[0], wv[1], wv[2], wv[3]);
+  *reinterpret_cast<float4*>(v + i4) = make_float4(vv[0], vv[1], vv[2], vv[3]);
+  if (zero_grad) *reinterpret_cast<float4*>(g + i4) = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (wb) *reinterpret_cast<uint2*>(wb + i4) = make_uint2(pack_bf16x2(wv[0], wv[1]), pack_bf16x2(wv[2], wv[3]));
+}
+
+int sgd_step(float* w, float* g, float* v, void* wb, size_t n, float lr, float momentum, float wd, int first,
+             int zero_grad, cudaStream_t st) {
+  if (!w || !g || !v || n % 4) return DBX_ERR_ARG;
+  sgd_step_kernel<<<grid_for(n / 4, 256), 256, 0, st>>>(w, g, v, (bf16*)wb, n, lr, momentum, wd, first, zero_grad);
+  return (int)cudaGetLastError();
+}
+
+__global__ void cast_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, size_t n) {
+  const size_t i4 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i4 >= n) return;
+  const float4 f = *reinterpret_cast<const float4*>(src + i4);
+  *reinterpret_cast<uint2*>(dst + i4) = make_uint2(pack_bf16x2(f.x, f.y), pack_bf16x2(f.z, f.w));
+}
+
+int cast_bf16(const float* src, void* dst, size_t n, cudaStream_t st) {
+  if (!src || !dst || n % 4) return DBX_ERR_ARG;
+  cast_bf16_kernel<<<grid_for(n / 4, 256), 256, 0, st>>>(src, (bf16*)dst, n);
+  return (int)cudaGetLastError();
+}
+
+// Zero the off-diagonal blocks of the block-diagonal conv5_2 gradient: row o belongs to head `head_of_row[o]`,
+// whose K range is [head*512, head*512+512).
+struct HeadRows { int nh; int start[5]; };  // head h owns rows [start[h], start[h+1])
+__global__ void blockdiag_mask_kernel(float* __restrict__ g, int rows, int ld, HeadRows hr) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)rows * ld) return;
+  const int o = (int)(idx / ld), k = (int)(idx % ld);
+  int h = -1;
+  for (int j = 0; j < hr.nh; ++j) if (o >= hr.start[j] && o < hr.start[j + 1]) h = j;
+  if (h < 0 || k / 512 != h) g[idx] = 0.f;
+}
+
+int blockdiag_mask(float* g, int rows, int ld, int nh, const int* start, cudaStream_t st) {
+  HeadRows hr; hr.nh = nh;
+  for (int j = 0; j < 5; ++j) hr.start[j] = j <= nh ? start[j] : 0;
+  blockdiag_mask_kernel<<<grid_for((size_t)rows * ld, 256), 256, 0, st>>>(g, rows, ld, hr);
+  return (int)cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------ dropout mask
+// nn.Dropout(p=0.5) in train mode (DenseBox.py:160,176): keep-mask scaled by 2, Philox4x32-10 counter RNG.
+__device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += 0x9E3779B9u; key.y += 0xBB67AE85u;
+  }
+  return ctr;
+}
+
+__global__ void dropout_mask_kernel(bf16* __restrict__ mask, size_t n8, unsigned long long seed,
+                                    unsigned long long offset) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n8) return;
+  const unsigned long long ctr = idx + offset;
+  const uint4 r = philox4x32(make_uint4((uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, 0u),
+                             make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  const uint32_t two = 0x4000u;  // bf16(2.0)
+  uint32_t w[4] = {r.x, r.y, r.z, r.w}, o[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) o[j] = ((w[j] & 0x8000u) ? two : 0u) | ((w[j] & 0x80000000u) ? (two << 16) : 0u);
+  reinterpret_cast<uint4*>(mask)[idx] = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+int dropout_mask(void* mask, size_t n, unsigned long long seed, unsigned long long offset, cudaStream_t st) {
+  if (!mask || n % 8) return DBX_ERR_ARG;
+  dropout_mask_kernel<<<grid_for(n / 8, 256), 256, 0, st>>>((bf16*)mask, n / 8, seed, offset);
+  return (int)cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------ refine glue
+// fusion_2 = cat(landmarks, scores) -> MaxPool2d(2) (DenseBox.py:464-465). head: fp32 [N,H,W,HC] with ch0 = score,
+// ch5..8 = landmark heat-maps.  pooled: bf16 [N,H/2,W/2,64], channels 0..3 = landmarks, 4 = score, 5..63 zero.
+__global__ void refine_pool_pack_kernel(const float* __restrict__ head, int HC, bf16* __restrict__ pooled, int N,
+                                        int H, int W) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int PH = H / 2, PW = W / 2;
+  if (idx >= (size_t)N * PH * PW) return;
+  const int px = (int)(idx % PW), py = (int)((idx / PW) % PH), n = (int)(idx / ((size_t)PW * PH));
+  float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const int src_ch[5] = {5, 6, 7, 8, 0};
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    float m = -INFINITY;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int y = 2 * py + (q >> 1), x = 2 * px + (q & 1);
+      m = fmaxf(m, __ldg(head + (((size_t)n * H + y) * W + x) * HC + src_ch[k]));
+    }
+    f[k] = m;
+  }
+  *reinterpret_cast<uint4*>(pooled + idx * 64) = pack8(f);
+}
+
+int refine_pool_pack(const float* head, int HC, void* pooled, int N, int H, int W, cudaStream_t st) {
+  if (!head || !pooled || H % 2 || W % 2 || HC < 9) return DBX_ERR_ARG;
+  refine_pool_pack_kernel<<<grid_for((size_t)N * (H / 2) * (W / 2), 256), 256, 0, st>>>(head, HC, (bf16*)pooled, N, H,
+                                                                                       W);
+  return (int)cudaGetLastError();
+}
+
+// Backward of the above: route dpooled[:, 0..4] to the first arg-max of each 2x2 window and ADD it into the head
+// gradient (bf16 [N,H,W,64], channels as in `head`) that the loss kernel has already written.
+__global__ void refine_pool_bwd_kernel(const float* __restrict__ head, int HC, const bf16* __restrict__ dpooled,
+                                       bf16* __restrict__ dhead, int N, int H, int W) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int PH = H / 2, PW = W / 2;
+  if (idx >= (size_t)N * PH * PW) return;
+  const int px = (int)(idx % PW), py = (int)((idx / PW) % PH), n = (int)(idx / ((size_t)PW * PH));
+  float g[8];
+  unpack8(ldg16(dpooled + idx * 64), g);
+  const int src_ch[5] = {5, 6, 7, 8, 0};
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    int arg = 0; float m = -INFINITY;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int y = 2 * py + (q >> 1), x = 2 * px + (q & 1);
+      const float v = __ldg(head + (((size_t)n * H + y) * W + x) * HC + src_ch[k]);
+      if (v > m) { m = v; arg = q; }
+    }
+    const int y = 2 * py + (arg >> 1), x = 2 * px + (arg & 1);
+    bf16* p = dhead + (((size_t)n * H + y) * W + x) * 64 + src_ch[k];
+    *p = __float2bfloat16_rn(__bfloat162float(*p) + g[k]);
+  }
+}
+
+int refine_pool_bwd(const float* head, int HC, const void* dpooled, void* dhead, int N, int H, int W, cudaStream_t st) {
+  if (!head || !dpooled || !dhead || H % 2 || W % 2 || HC < 9) return DBX_ERR_ARG;
+  refine_pool_bwd_kernel<<<grid_for((size_t)N * (H / 2) * (W / 2), 256), 256, 0, st>>>(
+      head, HC, (const bf16*)dpooled, (bf16*)dhead, N, H, W);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace dbx

@@ -1,0 +1,529 @@
+// densebox_b200 — the network engine: owns the HBM layout of one DenseBox{,LM,LMLOC} replica inside a caller-provided
+// workspace and sequences the kernels for forward (DenseBox.py:180-228 / :412-473 / :674-738), the fused loss and
+// the hand-written backward (the autograd graph of DenseBox.py:2925), plus the fused SGD step (:2926).
+//
+// HBM layout (all activations NHWC bf16, 64-byte aligned regions carved from the workspace):
+//   col0[N,H,W,64] -> a11,a12[N,H,W,64] -> p1 -> a21,a22[.,128] -> p2 -> a31,a32[.,256]
+//   fusion[N,H/4,W/4,768] = [ upsample(conv4_4) : 512 | conv3_4 : 256 ]   (torch.cat is free: producers write here)
+//   p3 -> a41..a44[.,512];  hd[N,H/4,W/4,512*heads] (post-dropout), head_out fp32 [N,H/4,W/4,16|32]
+//   refine: rp[.,H/8,W/8,64] -> r1 -> r2 -> rup[N,H/4,W/4,64] -> rf_out fp32 [.,16]
+//   one gradient buffer per activation (d_*), parameters as flat fp32 master / grad / momentum + bf16 GEMM copies.
+#include "dbx_common.h"
+#include <string.h>
+#include <string>
+#include <vector>
+
+namespace dbx {
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+static int round_up(int v, int a) { return (v + a - 1) / a * a; }
+
+struct Group {  // one GEMM weight matrix, K-major [rows][ld]
+  std::string name;
+  int rows = 0, ld = 0, T = 1, cin_pad = 0, kpad = 0;
+  size_t w_off = 0, b_off = 0, wd_off = 0;
+  bool need_dgrad = false;
+};
+struct Param {  // one torch tensor pair (weight, bias) placed inside a group
+  std::string name;
+  int cout, cin, R, S;
+  int grp;
+  long rowK, kK;
+  int cin_pad;
+};
+
+struct Buf { std::string name; size_t off, bytes; };
+
+struct Net {
+  int variant, N, H, W, train;
+  int nh, HC;            // heads, head_out channels
+  int ch_start[5];       // rows of conv5_2 group owned by head h
+  std::vector<Group> groups;
+  std::vector<Param> params;
+  std::vector<Buf> bufs;
+  char* ws = nullptr;
+  size_t ws_bytes = 0;
+  size_t flat_n = 0;     // fp32 elements in the flat parameter buffer (weights then biases)
+  size_t wd_n = 0;       // bf16 elements in the dgrad-layout buffer
+  bool forward_done = false, loss_done = false;
+  int sgd_steps = 0;
+
+  // ---- layout
+  size_t cursor = 0;
+  size_t add_buf(const char* name, size_t bytes) {
+    cursor = align_up(cursor, 256);
+    bufs.push_back({name, cursor, bytes});
+    cursor += bytes;
+    return bufs.back().off;
+  }
+  void* buf(const char* name, size_t* bytes = nullptr) const {
+    for (auto& b : bufs)
+      if (b.name == name) { if (bytes) *bytes = b.bytes; return ws ? ws + b.off : (void*)b.off; }
+    return nullptr;
+  }
+  int group_id(const char* name) const {
+    for (size_t i = 0; i < groups.size(); ++i) if (groups[i].name == name) return (int)i;
+    return -1;
+  }
+  int param_id(const char* name) const {
+    for (size_t i = 0; i < params.size(); ++i) if (params[i].name == name) return (int)i;
+    return -1;
+  }
+  Act act(const char* name, int h, int w, int C, int cs = 0, int coff = 0) const {
+    Act a; a.ptr = buf(name); a.N = N; a.H = h; a.W = w; a.C = C; a.cs = cs ? cs : C; a.coff = coff; return a;
+  }
+  float* W32() const { return (float*)buf("w32"); }
+  float* G32() const { return (float*)buf("g32"); }
+  float* V32() const { return (float*)buf("v32"); }
+  __nv_bfloat16* WK() const { return (__nv_bfloat16*)buf("wk"); }
+  __nv_bfloat16* WD() const { return (__nv_bfloat16*)buf("wd"); }
+
+  void add_group(const char* name, int rows, int T, int cin_pad, bool dgrad) {
+    Group g; g.name = name; g.rows = rows; g.T = T; g.cin_pad = cin_pad; g.ld = T * cin_pad;
+    g.kpad = round_up(rows, 64); g.need_dgrad = dgrad;
+    groups.push_back(g);
+  }
+  void add_param(const char* name, int cout, int cin, int R, int S, const char* grp, long rowK, long kK, int cin_pad) {
+    params.push_back({name, cout, cin, R, S, group_id(grp), rowK, kK, cin_pad});
+  }
+
+  void build(int variant_, int N_, int H_, int W_, int train_) {
+    variant = variant_; N = N_; H = H_; W = W_; train = train_;
+    nh = variant == 0 ? 2 : (variant == 1 ? 3 : 4);
+    HC = variant == 2 ? 32 : 16;
+    const int starts[5] = {0, 1, 5, 9, 17};
+    for (int i = 0; i < 5; ++i) ch_start[i] = starts[i];
+    // ---- GEMM groups
+    add_group("conv1_1", 64, 1, 64, false);
+    add_group("conv1_2", 64, 9, 64, true);
+    add_group("conv2_1", 128, 9, 64, true);
+    add_group("conv2_2", 128, 9, 128, true);
+    add_group("conv3_1", 256, 9, 128, true);
+    add_group("conv3_2", 256, 9, 256, true);
+    add_group("conv3_4", 256, 9, 256, true);
+    add_group("conv4_1", 512, 9, 256, true);
+    add_group("conv4_2", 512, 9, 512, true);
+    add_group("conv4_3", 512, 9, 512, true);
+    add_group("conv4_4", 512, 9, 512, true);
+    add_group("heads1", 512 * nh, 1, 768, true);
+    add_group("heads2", HC, 1, 512 * nh, true);
+    if (variant >= 1) {
+      add_group("conv6_1_det", 64, 9, 64, true);
+      add_group("conv6_2_det", 64, 25, 64, true);
+      add_group("conv6_3_det", 16, 1, 64, true);
+    }
+    size_t off = 0, wd = 0;
+    for (auto& g : groups) { g.w_off = off; off += align_up((size_t)g.rows * g.ld, 64); }
+    for (auto& g : groups) { g.b_off = off; off += align_up((size_t)g.rows, 64); }
+    flat_n = off;
+    for (auto& g : groups)
+      if (g.need_dgrad) { g.wd_off = wd; wd += align_up((size_t)g.cin_pad * g.T * g.kpad, 64); }
+    wd_n = wd;
+    // ---- torch tensors -> placement
+    add_param("conv1_1", 64, 3, 3, 3, "conv1_1", 0, 0, 3);
+    add_param("conv1_2", 64, 64, 3, 3, "conv1_2", 0, 0, 64);
+    add_param("conv2_1", 128, 64, 3, 3, "conv2_1", 0, 0, 64);
+    add_param("conv2_2", 128, 128, 3, 3, "conv2_2", 0, 0, 128);
+    add_param("conv3_1", 256, 128, 3, 3, "conv3_1", 0, 0, 128);
+    add_param("conv3_2", 256, 256, 3, 3, "conv3_2", 0, 0, 256);
+    add_param("conv3_4", 256, 256, 3, 3, "conv3_4", 0, 0, 256);
+    add_param("conv4_1", 512, 256, 3, 3, "conv4_1", 0, 0, 256);
+    add_param("conv4_2", 512, 512, 3, 3, "conv4_2", 0, 0, 512);
+    add_param("conv4_3", 512, 512, 3, 3, "conv4_3", 0, 0, 512);
+    add_param("conv4_4", 512, 512, 3, 3, "conv4_4", 0, 0, 512);
+    const char* hn[4] = {"det", "loc", "landmark", "lmloc"};
+    const int hc[4] = {1, 4, 4, 8};
+    for (int h = 0; h < nh; ++h) {
+      add_param((std::string("conv5_1_") + hn[h]).c_str(), 512, 768, 1, 1, "heads1", 512L * h, 0, 768);
+      add_param((std::string("conv5_2_") + hn[h]).c_str(), hc[h], 512, 1, 1, "heads2", ch_start[h], 512L * h, 512 * nh);
+    }
+    if (variant >= 1) {
+      add_param("conv6_1_det", 64, 5, 3, 3, "conv6_1_det", 0, 0, 64);
+      add_param("conv6_2_det", 64, 64, 5, 5, "conv6_2_det", 0, 0, 64);
+      add_param("conv6_3_det", 1, 64, 1, 1, "conv6_3_det", 0, 0, 64);
+    }
+    // ---- workspace regions
+    const size_t px1 = (size_t)N * H * W, px2 = px1 / 4, px4 = px1 / 16, px8 = px1 / 64;
+    add_buf("w32", flat_n * 4);
+    add_buf("wk", flat_n * 2);
+    add_buf("wd", wd_n * 2);
+    add_buf("scalars", 256);  // [0] loss f32, [1] counter u32, [2..3] info i32, [16..] loss_partial
+    add_buf("loss_partial", (size_t)N * 4);
+    add_buf("col0", px1 * 64 * 2);
+    add_buf("a11", px1 * 64 * 2); add_buf("a12", px1 * 64 * 2); add_buf("p1", px2 * 64 * 2);
+    add_buf("a21", px2 * 128 * 2); add_buf("a22", px2 * 128 * 2); add_buf("p2", px4 * 128 * 2);
+    add_buf("a31", px4 * 256 * 2); add_buf("a32", px4 * 256 * 2); add_buf("fusion", px4 * 768 * 2);
+    add_buf("p3", px8 * 256 * 2);
+    add_buf("a41", px8 * 512 * 2); add_buf("a42", px8 * 512 * 2); add_buf("a43", px8 * 512 * 2);
+    add_buf("a44", px8 * 512 * 2);
+    add_buf("hd", px4 * 512 * nh * 2);
+    add_buf("head_out", px4 * HC * 4);
+    const int h4 = H / 4, w4 = W / 4, h8 = H / 8, w8 = W / 8;
+    if (variant >= 1) {
+      add_buf("rp", px8 * 64 * 2);
+      add_buf("r1", (size_t)N * (h8 - 2) * (w8 - 2) * 64 * 2);
+      add_buf("r2", (size_t)N * (h8 - 6) * (w8 - 6) * 64 * 2);
+      add_buf("rup", px4 * 64 * 2);
+      add_buf("rf_out", px4 * 16 * 4);
+    }
+    if (train) {
+      add_buf("g32", flat_n * 4);
+      add_buf("v32", flat_n * 4);
+      add_buf("drop", px4 * 512 * nh * 2);
+      add_buf("d_head", px4 * 64 * 2);
+      add_buf("d_hd", px4 * 512 * nh * 2);
+      add_buf("d_fusion", px4 * 768 * 2);
+      add_buf("d_a44", px8 * 512 * 2); add_buf("d_a43", px8 * 512 * 2); add_buf("d_a42", px8 * 512 * 2);
+      add_buf("d_a41", px8 * 512 * 2); add_buf("d_p3", px8 * 256 * 2);
+      add_buf("d_a34", px4 * 256 * 2); add_buf("d_a32", px4 * 256 * 2); add_buf("d_a31", px4 * 256 * 2);
+      add_buf("d_p2", px4 * 128 * 2);
+      add_buf("d_a22", px2 * 128 * 2); add_buf("d_a21", px2 * 128 * 2); add_buf("d_p1", px2 * 64 * 2);
+      add_buf("d_a12", px1 * 64 * 2); add_buf("d_a11", px1 * 64 * 2);
+      if (variant >= 1) {
+        add_buf("d_rf", px4 * 64 * 2);
+        add_buf("d_rup", px4 * 64 * 2);
+        add_buf("d_r2", (size_t)N * (h8 - 6) * (w8 - 6) * 64 * 2);
+        add_buf("d_r1", (size_t)N * (h8 - 2) * (w8 - 2) * 64 * 2);
+        add_buf("d_rp", px8 * 64 * 2);
+      }
+    }
+    (void)h4; (void)w4;
+    ws_bytes = align_up(cursor, 256);
+  }
+
+  const __nv_bfloat16* wk_of(const char* g) const { return WK() + groups[group_id(g)].w_off; }
+  const __nv_bfloat16* wd_of(const char* g) const { return WD() + groups[group_id(g)].wd_off; }
+  const float* bias_of(const char* g) const { return W32() + groups[group_id(g)].b_off; }
+  float* gw_of(const char* g) const { return G32() + groups[group_id(g)].w_off; }
+  float* gb_of(const char* g) const { return G32() + groups[group_id(g)].b_off; }
+
+  // ---- one-time initialisation of the workspace (zero padding lanes, counters)
+  int init(cudaStream_t st) {
+    cudaError_t e = cudaMemsetAsync(ws, 0, ws_bytes, st);
+    return (int)e;
+  }
+
+  // ---- parameters
+  int set_param(const char* name, int is_bias, const float* src, long s_co, long s_ci, long s_r, long s_s,
+                cudaStream_t st) {
+    const int id = param_id(name);
+    if (id < 0 || !src) return DBX_ERR_ARG;
+    const Param& p = params[id];
+    const Group& g = groups[p.grp];
+    if (is_bias) {
+      cudaError_t e = cudaMemcpy2DAsync(W32() + g.b_off + p.rowK, 4, src, (size_t)s_co * 4, 4, p.cout,
+                                        cudaMemcpyDeviceToDevice, st);
+      return (int)e;
+    }
+    return pack_weights(src, p.cout, p.cin, p.R, p.S, s_co, s_ci, s_r, s_s, WK() + g.w_off, g.ld, p.rowK, p.kK,
+                        p.cin_pad, nullptr, 0, 0, 0, 0, W32() + g.w_off, st);
+  }
+  int get_tensor(const char* name, int is_bias, int which, float* dst, long s_co, long s_ci, long s_r, long s_s,
+                 cudaStream_t st) {
+    const int id = param_id(name);
+    if (id < 0 || !dst) return DBX_ERR_ARG;
+    if (which == 1 && !train) return DBX_ERR_STATE;
+    const Param& p = params[id];
+    const Group& g = groups[p.grp];
+    const float* base = which == 0 ? W32() : G32();
+    if (is_bias) {
+      cudaError_t e = cudaMemcpy2DAsync(dst, (size_t)s_co * 4, base + g.b_off + p.rowK, 4, 4, p.cout,
+                                        cudaMemcpyDeviceToDevice, st);
+      return (int)e;
+    }
+    return unpack_weights(base + g.w_off, g.ld, p.rowK, p.kK, p.cin_pad, dst, p.cout, p.cin, p.R, p.S, s_co, s_ci,
+                          s_r, s_s, st);
+  }
+  // bf16 dgrad-layout copies of every filter (call after the weights changed, before backward)
+  int refresh_dgrad(cudaStream_t st) {
+    for (auto& g : groups) {
+      if (!g.need_dgrad) continue;
+      int rc = transpose_dgrad(WK() + g.w_off, WD() + g.wd_off, g.rows, g.T, g.cin_pad, g.kpad, st);
+      if (rc) return rc;
+    }
+    return DBX_OK;
+  }
+
+  // ---- forward
+  int conv(const Act& x, const char* grp, int R, int pad, const Act& out, bool relu, const void* aux, int aux_cs,
+           int aux_mode, bool fp32, int block_n, cudaStream_t st) {
+    ConvEpilogue e;
+    e.bias = bias_of(grp); e.relu = relu ? 1 : 0; e.aux = aux; e.aux_cs = aux_cs; e.aux_mode = aux_mode;
+    e.out_fp32 = fp32 ? 1 : 0;
+    return conv_fprop(x, wk_of(grp), R, R, pad, out, e, block_n, st);
+  }
+  int dgrad(const Act& dy, const char* grp, int R, int pad, const Act& dx, const Act* relu_y, cudaStream_t st) {
+    ConvEpilogue e;
+    if (relu_y) { e.aux = relu_y->ptr; e.aux_cs = relu_y->cs; e.aux_coff = relu_y->coff; e.aux_mode = 1; }
+    return conv_fprop(dy, wd_of(grp), R, R, R - 1 - pad, dx, e, 0, st);
+  }
+  int wgrad(const Act& x, const Act& dy, const char* grp, int R, int pad, cudaStream_t st) {
+    int rc = conv_wgrad(x, dy, R, R, pad, gw_of(grp), 0, st);
+    if (rc) return rc;
+    return colsum(dy, gb_of(grp), st);
+  }
+
+#define DBX_TRY(expr) do { int _rc = (expr); if (_rc) return _rc; } while (0)
+
+  // dropout_mode: 0 = eval (identity), 1 = draw a Philox mask (seed, offset), 2 = use the mask already in `drop`
+  int forward(const float* x, int dropout_mode, unsigned long long seed, unsigned long long offset, cudaStream_t st) {
+    if (!x) return DBX_ERR_ARG;
+    if (dropout_mode && !train) return DBX_ERR_STATE;
+    const int h2 = H / 2, w2 = W / 2, h4 = H / 4, w4 = W / 4, h8 = H / 8, w8 = W / 8;
+    Act col0 = act("col0", H, W, 64), a11 = act("a11", H, W, 64), a12 = act("a12", H, W, 64);
+    Act p1 = act("p1", h2, w2, 64), a21 = act("a21", h2, w2, 128), a22 = act("a22", h2, w2, 128);
+    Act p2 = act("p2", h4, w4, 128), a31 = act("a31", h4, w4, 256), a32 = act("a32", h4, w4, 256);
+    Act fus = act("fusion", h4, w4, 768), fus_up = act("fusion", h4, w4, 512, 768, 0);
+    Act a34 = act("fusion", h4, w4, 256, 768, 512);
+    Act p3 = act("p3", h8, w8, 256), a41 = act("a41", h8, w8, 512), a42 = act("a42", h8, w8, 512);
+    Act a43 = act("a43", h8, w8, 512), a44 = act("a44", h8, w8, 512);
+    Act hd = act("hd", h4, w4, 512 * nh), ho = act("head_out", h4, w4, HC);
+    DBX_TRY(im2col3x3_c3(x, col0.ptr, N, H, W, st));
+    DBX_TRY(conv(col0, "conv1_1", 1, 0, a11, true, nullptr, 0, 0, false, 0, st));
+    DBX_TRY(conv(a11, "conv1_2", 3, 1, a12, true, nullptr, 0, 0, false, 0, st));
+    DBX_TRY(maxpool2x2_fwd(a12, p1, st));
+    DBX_TRY(conv(p1, "conv2_1", 3, 1, a21, true, nullptr, 0, 0, false, 0, st));
+    DBX_TRY(conv(a21, "conv2_2", 3, 1, a22, true, nullptr, 0, 0, false, 0, st));
+    DBX_TRY(maxpool2x2_fwd(a22, p2, st));
+    DBX_TRY(conv(p2, "conv3_1", 3, 1, a31, true, nullptr, 0, 0, false, 0, st));
+    DBX_TRY(conv(a31, "conv3_2", 3, 1, a32, true, nullptr, 0, 0, false, 0, st));
+    DBX_TRY(conv(a32, "conv3_4", 3, 1, a34, true, nullptr, 0, 0, false, 0, st));  // conv3_3 skipped (:193-195)
+    DBX_TRY(maxpool2x2_fwd(a34, p3, st));
+    DBX_TRY(conv(p3, "conv4_1", 3, 1, a41, true, nullptr, 0, 0, false, 0, st));
+    DBX_TRY(conv(a41, "conv4_2", 3, 1, a42, true, nullptr, 0, 0, false, 0, st));
+    DBX_TRY(conv(a42, "conv4_3", 3, 1, a43, true, nullptr, 0, 0, false, 0, st));
+    DBX_TRY(conv(a43, "conv4_4", 3, 1, a44, true, nullptr, 0, 0, false, 0, st));
+    DBX_TRY(upsample_bilinear_fwd(a44, fus_up, st));
+    const void* drop = nullptr;
+    if (dropout_mode) {
+      drop = buf("drop");
+      if (dropout_mode == 1) DBX_TRY(dropout_mask(buf("drop"), (size_t)N * h4 * w4 * 512 * nh, seed, offset, st));
+    }
+    DBX_TRY(conv(fus, "heads1", 1, 0, hd, false, drop, 512 * nh, drop ? 2 : 0, false, 0, st));
+    DBX_TRY(conv(hd, "heads2", 1, 0, ho, false, nullptr, 0, 0, true, 0, st));
+    if (variant >= 1) {
+      Act rp = act("rp", h8, w8, 64), r1 = act("r1", h8 - 2, w8 - 2, 64), r2 = act("r2", h8 - 6, w8 - 6, 64);
+      Act rup = act("rup", h4, w4, 64), rf = act("rf_out", h4, w4, 16);
+      DBX_TRY(refine_pool_pack((const float*)ho.ptr, HC, rp.ptr, N, h4, w4, st));
+      DBX_TRY(conv(rp, "conv6_1_det", 3, 0, r1, false, nullptr, 0, 0, false, 0, st));
+      DBX_TRY(conv(r1, "conv6_2_det", 5, 0, r2, false, nullptr, 0, 0, false, 0, st));
+      DBX_TRY(upsample_bilinear_fwd(r2, rup, st));
+      DBX_TRY(conv(rup, "conv6_3_det", 1, 0, rf, false, nullptr, 0, 0, true, 0, st));
+    }
+    dropout_used = dropout_mode != 0;
+    forward_done = true;
+    return DBX_OK;
+  }
+  bool dropout_used = false;
+
+  // ---- loss (+ gradients w.r.t. the head outputs)
+  int loss(const float* bbox, const float* vertices, const float* labels, const long long* rand_idx, int rand_stride,
+           const long long* lm_rand_idx, float lambda_loc, float lambda_det, float lambda_lm, int global_pos,
+           int global_batch, const int* global_pos_ptr, int clamp_lm, float* d_head_f32, float* d_rf_f32,
+           unsigned char* mask_out, unsigned char* lm_mask_out, cudaStream_t st) {
+    if (!forward_done) return DBX_ERR_STATE;
+    if (H != 240 || W != 240) return DBX_ERR_ARG;  // the reference loss is defined on 60x60 maps only (:1379)
+    LossParams p{};
+    p.head = (const float*)buf("head_out"); p.HC = HC;
+    p.rf = variant >= 1 ? (const float*)buf("rf_out") : nullptr; p.RC = 16;
+    p.bbox = bbox; p.vertices = vertices; p.labels = labels;
+    p.rand_idx = rand_idx; p.rand_stride = rand_stride; p.lm_rand_idx = lm_rand_idx;
+    p.variant = variant; p.lambda_loc = lambda_loc; p.lambda_det = lambda_det; p.lambda_lm = lambda_lm;
+    p.global_pos = global_pos; p.global_batch = global_batch; p.global_pos_ptr = global_pos_ptr;
+    p.clamp_lm = clamp_lm; p.B = N;
+    float* sc = (float*)buf("scalars");
+    p.loss = sc; p.counter = (unsigned int*)(sc + 1); p.info = (int*)(sc + 2);
+    p.loss_partial = (float*)buf("loss_partial");
+    p.d_head = train ? (__nv_bfloat16*)buf("d_head") : nullptr;
+    p.d_rf = (train && variant >= 1) ? (__nv_bfloat16*)buf("d_rf") : nullptr;
+    p.d_head_f32 = d_head_f32; p.d_rf_f32 = d_rf_f32; p.mask_out = mask_out; p.lm_mask_out = lm_mask_out;
+    DBX_TRY(loss_fwd_bwd(p, st));
+    loss_done = true;
+    return DBX_OK;
+  }
+
+  // ---- backward: d_head / d_rf (bf16, written by loss() or by the caller) -> parameter gradients in g32 (+=)
+  int backward(cudaStream_t st) {
+    if (!train || !forward_done) return DBX_ERR_STATE;
+    const int h2 = H / 2, w2 = W / 2, h4 = H / 4, w4 = W / 4, h8 = H / 8, w8 = W / 8;
+    Act col0 = act("col0", H, W, 64), a11 = act("a11", H, W, 64), a12 = act("a12", H, W, 64);
+    Act p1 = act("p1", h2, w2, 64), a21 = act("a21", h2, w2, 128), a22 = act("a22", h2, w2, 128);
+    Act p2 = act("p2", h4, w4, 128), a31 = act("a31", h4, w4, 256), a32 = act("a32", h4, w4, 256);
+    Act fus = act("fusion", h4, w4, 768), a34 = act("fusion", h4, w4, 256, 768, 512);
+    Act p3 = act("p3", h8, w8, 256), a41 = act("a41", h8, w8, 512), a42 = act("a42", h8, w8, 512);
+    Act a43 = act("a43", h8, w8, 512), a44 = act("a44", h8, w8, 512);
+    Act hd = act("hd", h4, w4, 512 * nh);
+    Act d_head64 = act("d_head", h4, w4, 64), d_headC = act("d_head", h4, w4, HC, 64, 0);
+    Act d_hd = act("d_hd", h4, w4, 512 * nh), d_fus = act("d_fusion", h4, w4, 768);
+    Act d_fus_up = act("d_fusion", h4, w4, 512, 768, 0), d_fus_34 = act("d_fusion", h4, w4, 256, 768, 512);
+    Act d_a44 = act("d_a44", h8, w8, 512), d_a43 = act("d_a43", h8, w8, 512), d_a42 = act("d_a42", h8, w8, 512);
+    Act d_a41 = act("d_a41", h8, w8, 512), d_p3 = act("d_p3", h8, w8, 256);
+    Act d_a34 = act("d_a34", h4, w4, 256), d_a32 = act("d_a32", h4, w4, 256), d_a31 = act("d_a31", h4, w4, 256);
+    Act d_p2 = act("d_p2", h4, w4, 128), d_a22 = act("d_a22", h2, w2, 128), d_a21 = act("d_a21", h2, w2, 128);
+    Act d_p1 = act("d_p1", h2, w2, 64), d_a12 = act("d_a12", H, W, 64), d_a11 = act("d_a11", H, W, 64);
+
+    if (variant >= 1) {
+      Act rp = act("rp", h8, w8, 64), r1 = act("r1", h8 - 2, w8 - 2, 64);
+      Act rup = act("rup", h4, w4, 64);
+      Act d_rf64 = act("d_rf", h4, w4, 64), d_rf16 = act("d_rf", h4, w4, 16, 64, 0);
+      Act d_rup = act("d_rup", h4, w4, 64), d_r2 = act("d_r2", h8 - 6, w8 - 6, 64);
+      Act d_r1 = act("d_r1", h8 - 2, w8 - 2, 64), d_rp = act("d_rp", h8, w8, 64);
+      DBX_TRY(wgrad(rup, d_rf16, "conv6_3_det", 1, 0, st));
+      DBX_TRY(dgrad(d_rf64, "conv6_3_det", 1, 0, d_rup, nullptr, st));
+      DBX_TRY(upsample_bilinear_bwd(d_rup, nullptr, d_r2, st));
+      DBX_TRY(wgrad(r1, d_r2, "conv6_2_det", 5, 0, st));
+      DBX_TRY(dgrad(d_r2, "conv6_2_det", 5, 0, d_r1, nullptr, st));
+      DBX_TRY(wgrad(rp, d_r1, "conv6_1_det", 3, 0, st));
+      DBX_TRY(dgrad(d_r1, "conv6_1_det", 3, 0, d_rp, nullptr, st));
+      DBX_TRY(refine_pool_bwd((const float*)buf("head_out"), HC, d_rp.ptr, d_head64.ptr, N, h4, w4, st));
+    }
+    // heads
+    DBX_TRY(wgrad(hd, d_headC, "heads2", 1, 0, st));
+    {
+      const Group& g = groups[group_id("heads2")];
+      DBX_TRY(blockdiag_mask(G32() + g.w_off, g.rows, g.ld, nh, ch_start, st));
+      ConvEpilogue e;
+      if (dropout_used) { e.aux = buf("drop"); e.aux_cs = 512 * nh; e.aux_mode = 2; }
+      DBX_TRY(conv_fprop(d_head64, wd_of("heads2"), 1, 1, 0, d_hd, e, 0, st));
+    }
+    DBX_TRY(wgrad(fus, d_hd, "heads1", 1, 0, st));
+    DBX_TRY(dgrad(d_hd, "heads1", 1, 0, d_fus, nullptr, st));
+    // conv4 block
+    DBX_TRY(upsample_bilinear_bwd(d_fus_up, &a44, d_a44, st));
+    DBX_TRY(wgrad(a43, d_a44, "conv4_4", 3, 1, st));
+    DBX_TRY(dgrad(d_a44, "conv4_4", 3, 1, d_a43, &a43, st));
+    DBX_TRY(wgrad(a42, d_a43, "conv4_3", 3, 1, st));
+    DBX_TRY(dgrad(d_a43, "conv4_3", 3, 1, d_a42, &a42, st));
+    DBX_TRY(wgrad(a41, d_a42, "conv4_2", 3, 1, st));
+    DBX_TRY(dgrad(d_a42, "conv4_2", 3, 1, d_a41, &a41, st));
+    DBX_TRY(wgrad(p3, d_a41, "conv4_1", 3, 1, st));
+    DBX_TRY(dgrad(d_a41, "conv4_1", 3, 1, d_p3, nullptr, st));
+    // conv3 block: pool3 backward + the concat branch of conv3_4, then ReLU mask
+    DBX_TRY(maxpool2x2_bwd(a34, d_p3, &d_fus_34, d_a34, st));
+    DBX_TRY(wgrad(a32, d_a34, "conv3_4", 3, 1, st));
+    DBX_TRY(dgrad(d_a34, "conv3_4", 3, 1, d_a32, &a32, st));
+    DBX_TRY(wgrad(a31, d_a32, "conv3_2", 3, 1, st));
+    DBX_TRY(dgrad(d_a32, "conv3_2", 3, 1, d_a31, &a31, st));
+    DBX_TRY(wgrad(p2, d_a31, "conv3_1", 3, 1, st));
+    DBX_TRY(dgrad(d_a31, "conv3_1", 3, 1, d_p2, nullptr, st));
+    // conv2 block
+    DBX_TRY(maxpool2x2_bwd(a22, d_p2, nullptr, d_a22, st));
+    DBX_TRY(wgrad(a21, d_a22, "conv2_2", 3, 1, st));
+    DBX_TRY(dgrad(d_a22, "conv2_2", 3, 1, d_a21, &a21, st));
+    DBX_TRY(wgrad(p1, d_a21, "conv2_1", 3, 1, st));
+    DBX_TRY(dgrad(d_a21, "conv2_1", 3, 1, d_p1, nullptr, st));
+    // conv1 block
+    DBX_TRY(maxpool2x2_bwd(a12, d_p1, nullptr, d_a12, st));
+    DBX_TRY(wgrad(a11, d_a12, "conv1_2", 3, 1, st));
+    DBX_TRY(dgrad(d_a12, "conv1_2", 3, 1, d_a11, &a11, st));
+    DBX_TRY(wgrad(col0, d_a11, "conv1_1", 1, 0, st));
+    return DBX_OK;
+  }
+
+  int zero_grad(cudaStream_t st) {
+    if (!train) return DBX_ERR_STATE;
+    return (int)cudaMemsetAsync(G32(), 0, flat_n * 4, st);
+  }
+
+  int sgd(float lr, float momentum, float wd, cudaStream_t st) {
+    if (!train) return DBX_ERR_STATE;
+    DBX_TRY(sgd_step(W32(), G32(), V32(), WK(), flat_n, lr, momentum, wd, sgd_steps == 0 ? 1 : 0, 1, st));
+    ++sgd_steps;
+    return refresh_dgrad(st);
+  }
+};
+
+}  // namespace dbx
+
+// ------------------------------------------------------------------------------------------------ C ABI
+using namespace dbx;
+#include "../../include/densebox_b200.h"
+
+extern "C" {
+
+int dbx_net_workspace_bytes(int variant, int N, int H, int W, int train, size_t* bytes) {
+  if (!bytes || variant < 0 || variant > 2 || N <= 0 || H <= 0 || W <= 0 || H % 8 || W % 8) return DBX_ERR_ARG;
+  if (variant >= 1 && (H / 8 < 7 || W / 8 < 7)) return DBX_ERR_ARG;
+  Net n;
+  n.build(variant, N, H, W, train);
+  *bytes = n.ws_bytes;
+  return DBX_OK;
+}
+
+int dbx_net_create(int variant, int N, int H, int W, int train, void* workspace, size_t bytes, void* stream,
+                   void** handle) {
+  size_t need = 0;
+  int rc = dbx_net_workspace_bytes(variant, N, H, W, train, &need);
+  if (rc) return rc;
+  if (!workspace || !handle || ((uintptr_t)workspace & 255)) return DBX_ERR_ARG;
+  if (bytes < need) return DBX_ERR_WORKSPACE;
+  Net* n = new Net();
+  n->build(variant, N, H, W, train);
+  n->ws = (char*)workspace;
+  rc = n->init((cudaStream_t)stream);
+  if (rc) { delete n; return rc; }
+  *handle = n;
+  return DBX_OK;
+}
+
+int dbx_net_destroy(void* handle) { delete (Net*)handle; return DBX_OK; }
+
+int dbx_net_buffer(void* handle, const char* name, void** ptr, size_t* bytes) {
+  if (!handle || !name || !ptr) return DBX_ERR_ARG;
+  void* p = ((Net*)handle)->buf(name, bytes);
+  if (!p) return DBX_ERR_ARG;
+  *ptr = p;
+  return DBX_OK;
+}
+
+int dbx_net_head_channels(void* handle) { return handle ? ((Net*)handle)->HC : DBX_ERR_ARG; }
+long long dbx_net_param_elems(void* handle) { return handle ? (long long)((Net*)handle)->flat_n : DBX_ERR_ARG; }
+
+int dbx_net_set_param(void* handle, const char* name, int is_bias, const float* src, long s_co, long s_ci, long s_r,
+                      long s_s, void* stream) {
+  if (!handle) return DBX_ERR_ARG;
+  return ((Net*)handle)->set_param(name, is_bias, src, s_co, s_ci, s_r, s_s, (cudaStream_t)stream);
+}
+int dbx_net_get_param(void* handle, const char* name, int is_bias, float* dst, long s_co, long s_ci, long s_r,
+                      long s_s, void* stream) {
+  if (!handle) return DBX_ERR_ARG;
+  return ((Net*)handle)->get_tensor(name, is_bias, 0, dst, s_co, s_ci, s_r, s_s, (cudaStream_t)stream);
+}
+int dbx_net_get_grad(void* handle, const char* name, int is_bias, float* dst, long s_co, long s_ci, long s_r,
+                     long s_s, void* stream) {
+  if (!handle) return DBX_ERR_ARG;
+  return ((Net*)handle)->get_tensor(name, is_bias, 1, dst, s_co, s_ci, s_r, s_s, (cudaStream_t)stream);
+}
+int dbx_net_refresh_dgrad(void* handle, void* stream) {
+  if (!handle) return DBX_ERR_ARG;
+  return ((Net*)handle)->refresh_dgrad((cudaStream_t)stream);
+}
+int dbx_net_forward(void* handle, const float* x, int dropout_mode, unsigned long long seed,
+                    unsigned long long offset, void* stream) {
+  if (!handle) return DBX_ERR_ARG;
+  return ((Net*)handle)->forward(x, dropout_mode, seed, offset, (cudaStream_t)stream);
+}
+int dbx_net_loss(void* handle, const float* bbox, const float* vertices, const float* labels,
+                 const long long* rand_idx, int rand_stride, const long long* lm_rand_idx, float lambda_loc,
+                 float lambda_det, float lambda_lm, int global_pos, int global_batch, const int* global_pos_ptr,
+                 int clamp_lm, float* d_head_f32, float* d_rf_f32, unsigned char* mask_out,
+                 unsigned char* lm_mask_out, void* stream) {
+  if (!handle) return DBX_ERR_ARG;
+  return ((Net*)handle)->loss(bbox, vertices, labels, rand_idx, rand_stride, lm_rand_idx, lambda_loc, lambda_det,
+                              lambda_lm, global_pos, global_batch, global_pos_ptr, clamp_lm, d_head_f32, d_rf_f32,
+                              mask_out, lm_mask_out, (cudaStream_t)stream);
+}
+int dbx_net_backward(void* handle, void* stream) {
+  if (!handle) return DBX_ERR_ARG;
+  return ((Net*)handle)->backward((cudaStream_t)stream);
+}
+int dbx_net_zero_grad(void* handle, void* stream) {
+  if (!handle) return DBX_ERR_ARG;
+  return ((Net*)handle)->zero_grad((cudaStream_t)stream);
+}
+int dbx_net_sgd_step(void* handle, float lr, float momentum, float weight_decay, void* stream) {
+  if (!handle) return DBX_ERR_ARG;
+  return ((Net*)handle)->sgd(lr, momentum, weight_decay, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,150 @@
+"""Python handle on the native network engine (dbx_net_* in include/densebox_b200.h).
+
+torch is used for device memory (the workspace is one torch.uint8 tensor), streams and views of the engine's
+buffers; every computation is a call into libdensebox_b200.so.
+"""
+import ctypes
+
+import torch
+
+from ._lib import DbxError, check, lib, ptr, stream_ptr
+
+VARIANTS = {"densebox": 0, "lm": 1, "lmloc": 2}
+HEAD_NAMES = {0: ["det", "loc"], 1: ["det", "loc", "landmark"], 2: ["det", "loc", "landmark", "lmloc"]}
+BACKBONE = ["conv1_1", "conv1_2", "conv2_1", "conv2_2", "conv3_1", "conv3_2", "conv3_4", "conv4_1", "conv4_2",
+            "conv4_3", "conv4_4"]
+
+c_int, c_long, c_float, c_ull = ctypes.c_int, ctypes.c_long, ctypes.c_float, ctypes.c_ulonglong
+
+
+def unique_param_names(variant):
+    """Names of the (weight, bias) pairs the engine consumes, in the reference's naming (conv3_3 is unused)."""
+    v = VARIANTS[variant] if isinstance(variant, str) else variant
+    names = list(BACKBONE)
+    names += ["conv5_1_" + h for h in HEAD_NAMES[v]] + ["conv5_2_" + h for h in HEAD_NAMES[v]]
+    if v >= 1:
+        names += ["conv6_1_det", "conv6_2_det", "conv6_3_det"]
+    return names
+
+
+class NetEngine:
+    """One replica for a fixed input shape [N,3,H,W] on the current CUDA device."""
+
+    def __init__(self, variant, N, H, W, train=True, device=None):
+        if not torch.cuda.is_available():
+            raise DbxError("densebox_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.variant = VARIANTS[variant] if isinstance(variant, str) else int(variant)
+        self.N, self.H, self.W, self.train = N, H, W, bool(train)
+        self.device = torch.device(device if device is not None else torch.cuda.current_device())
+        L = lib()
+        nbytes = ctypes.c_size_t(0)
+        check(L.dbx_net_workspace_bytes(c_int(self.variant), c_int(N), c_int(H), c_int(W), c_int(int(self.train)),
+                                        ctypes.byref(nbytes)), "net_workspace_bytes")
+        self.workspace_bytes = nbytes.value
+        with torch.cuda.device(self.device):
+            self.ws = torch.empty(nbytes.value + 256, dtype=torch.uint8, device=self.device)
+            self._ws_off = (-self.ws.data_ptr()) % 256
+            h = ctypes.c_void_p(0)
+            check(L.dbx_net_create(c_int(self.variant), c_int(N), c_int(H), c_int(W), c_int(int(self.train)),
+                                   ctypes.c_void_p(self.ws.data_ptr() + self._ws_off), ctypes.c_size_t(nbytes.value),
+                                   stream_ptr(), ctypes.byref(h)), "net_create")
+        self.h = h
+        self.HC = L.dbx_net_head_channels(self.h)
+        self.h4, self.w4 = H // 4, W // 4
+        self._keep = []
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                lib().dbx_net_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    # ---- buffers as torch views (no copies)
+    def buffer(self, name, dtype, shape=None):
+        p, n = ctypes.c_void_p(0), ctypes.c_size_t(0)
+        check(lib().dbx_net_buffer(self.h, name.encode(), ctypes.byref(p), ctypes.byref(n)), "net_buffer(%s)" % name)
+        off = p.value - self.ws.data_ptr()
+        t = self.ws[off:off + n.value].view(dtype)
+        return t.view(shape) if shape is not None else t
+
+    def head_out(self):
+        return self.buffer("head_out", torch.float32, (self.N, self.h4, self.w4, self.HC))
+
+    def rf_out(self):
+        return self.buffer("rf_out", torch.float32, (self.N, self.h4, self.w4, 16))
+
+    def scalars(self):
+        return self.buffer("scalars", torch.float32)
+
+    def loss_value(self):
+        return self.scalars()[0]
+
+    def loss_info(self):
+        i = self.buffer("scalars", torch.int32)
+        return int(i[2]), int(i[3])
+
+    # ---- parameters
+    @staticmethod
+    def _strides(t):
+        s = list(t.stride()) + [0, 0, 0]
+        return [c_long(v) for v in s[:4]]
+
+    def set_param(self, name, weight, bias):
+        w = weight.detach()
+        b = bias.detach()
+        assert w.dtype == torch.float32 and w.is_cuda and b.dtype == torch.float32
+        L = lib()
+        check(L.dbx_net_set_param(self.h, name.encode(), c_int(0), ptr(w), *self._strides(w), stream_ptr()),
+              "set_param(%s.weight)" % name)
+        check(L.dbx_net_set_param(self.h, name.encode(), c_int(1), ptr(b), *self._strides(b), stream_ptr()),
+              "set_param(%s.bias)" % name)
+
+    def get_tensor(self, name, like_w, like_b, grad=False):
+        L = lib()
+        fn = L.dbx_net_get_grad if grad else L.dbx_net_get_param
+        w = torch.empty_like(like_w, dtype=torch.float32, memory_format=torch.contiguous_format)
+        b = torch.empty_like(like_b, dtype=torch.float32, memory_format=torch.contiguous_format)
+        check(fn(self.h, name.encode(), c_int(0), ptr(w), *self._strides(w), stream_ptr()), "get(%s.weight)" % name)
+        check(fn(self.h, name.encode(), c_int(1), ptr(b), *self._strides(b), stream_ptr()), "get(%s.bias)" % name)
+        return w, b
+
+    def refresh_dgrad(self):
+        check(lib().dbx_net_refresh_dgrad(self.h, stream_ptr()), "refresh_dgrad")
+
+    # ---- the path
+    def forward(self, x, dropout_mode=0, seed=0, offset=0):
+        assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()
+        assert tuple(x.shape) == (self.N, 3, self.H, self.W), (tuple(x.shape), (self.N, 3, self.H, self.W))
+        check(lib().dbx_net_forward(self.h, ptr(x), c_int(dropout_mode), c_ull(seed), c_ull(offset), stream_ptr()),
+              "net_forward")
+
+    def loss(self, bbox, vertices=None, labels=None, rand_idx=None, lm_rand_idx=None, lambda_loc=3.0, lambda_det=1.0,
+             lambda_lm=0.5, global_pos=-1, global_batch=-1, global_pos_dev=None, clamp_lm=False, d_head_f32=None,
+             d_rf_f32=None, mask_out=None, lm_mask_out=None):
+        for t, dt in ((bbox, torch.float32), (vertices, torch.float32), (labels, torch.float32),
+                      (rand_idx, torch.int64), (lm_rand_idx, torch.int64), (global_pos_dev, torch.int32)):
+            assert t is None or (t.is_cuda and t.dtype == dt and t.is_contiguous())
+        check(lib().dbx_net_loss(
+            self.h, ptr(bbox), ptr(vertices), ptr(labels), ptr(rand_idx),
+            c_int(rand_idx.shape[1] if rand_idx is not None else 0), ptr(lm_rand_idx), c_float(lambda_loc),
+            c_float(lambda_det), c_float(lambda_lm), c_int(global_pos), c_int(global_batch), ptr(global_pos_dev),
+            c_int(int(clamp_lm)), ptr(d_head_f32), ptr(d_rf_f32), ptr(mask_out), ptr(lm_mask_out), stream_ptr()),
+            "net_loss")
+
+    def backward(self):
+        check(lib().dbx_net_backward(self.h, stream_ptr()), "net_backward")
+
+    def zero_grad(self):
+        check(lib().dbx_net_zero_grad(self.h, stream_ptr()), "net_zero_grad")
+
+    def sgd_step(self, lr, momentum=0.9, weight_decay=5e-8):
+        check(lib().dbx_net_sgd_step(self.h, c_float(lr), c_float(momentum), c_float(weight_decay), stream_ptr()),
+              "net_sgd_step")
+
+    def flat_grads(self):
+        return self.buffer("g32", torch.float32)
+
+    def flat_params(self):
+        return self.buffer("w32", torch.float32)

@@ -1,0 +1,144 @@
+"""`DenseBoxTrainer` — the reference training-loop body (DenseBox.py:2836-2926 and its LM / LMLOC twins) as one native
+step: H2D of the batch, forward, fused loss, hand-written backward, gradient all-reduce (data parallel), SGD.
+
+The reference's loop crosses the host/device boundary 7+ times per step and synchronises twice; here nothing leaves
+the GPU between the input copy and the scalar loss.  With `use_cuda_graph=True` forward+loss+backward and the SGD
+update are replayed as two CUDA graphs; the NCCL all-reduce of the flat gradient buffer sits between them.
+Data parallel: one process per GPU, batch sharded by rank, gradient SUM all-reduce (the loss is a sum,
+DenseBox.py:2917), and the negative quota uses the batch-GLOBAL positive count (:2864-2868) via a 1-int all-reduce.
+"""
+import ctypes
+
+import torch
+
+from ._lib import check, lib, ptr, stream_ptr
+from .engine import NetEngine, unique_param_names
+
+c_int = ctypes.c_int
+
+
+class DenseBoxTrainer:
+    def __init__(self, net, batch_size, lr=1e-9, momentum=0.9, weight_decay=5e-8, lambda_loc=3.0, lambda_det=1.0,
+                 lambda_lm=0.5, patch=240, rand_width=256, process_group=None, use_cuda_graph=True, dropout=True,
+                 device=None, seed=0):
+        self.net = net
+        self.variant = net.variant
+        self.B = batch_size
+        self.lr, self.momentum, self.weight_decay = lr, momentum, weight_decay
+        self.lambdas = (lambda_loc, lambda_det, lambda_lm)
+        self.pg = process_group
+        self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
+        self.dropout = dropout
+        self.seed, self.step_no = seed, 0
+        self.device = torch.device(device if device is not None else torch.cuda.current_device())
+        self.eng = NetEngine(self.variant, batch_size, patch, patch, train=True, device=self.device)
+        dev = self.device
+        self.x = torch.zeros(batch_size, 3, patch, patch, device=dev)
+        self.bbox = torch.zeros(batch_size, 4, device=dev)
+        self.vertices = torch.zeros(batch_size, 8, device=dev)
+        self.labels = torch.ones(batch_size, device=dev)
+        self.rand = torch.zeros(batch_size, rand_width, dtype=torch.int64, device=dev)
+        self.lm_rand = torch.zeros(batch_size, 4, dtype=torch.int64, device=dev)
+        self.gpos = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.use_labels = False
+        self.use_graph = use_cuda_graph
+        self._graph_fb = self._graph_sgd = None
+        self._graph_lr = None
+        self.load_from_module()
+
+    # ---- parameters
+    def load_from_module(self):
+        for name in unique_param_names(self.variant):
+            w, b = self.net._wb(name)
+            self.eng.set_param(name, w.detach().to(self.device), b.detach().to(self.device))
+        self.eng.refresh_dgrad()
+        self.eng.zero_grad()
+
+    @torch.no_grad()
+    def store_to_module(self):
+        for name in unique_param_names(self.variant):
+            w, b = self.net._wb(name)
+            gw, gb = self.eng.get_tensor(name, w, b, grad=False)
+            w.copy_(gw)
+            b.copy_(gb)
+
+    # ---- one step
+    def _stage(self, dst, src):
+        if src is None:
+            return
+        src = torch.as_tensor(src)
+        dst.copy_(src.reshape(dst.shape) if src.numel() == dst.numel() else src, non_blocking=True)
+
+    def _fwd_loss_bwd(self):
+        e = self.eng
+        e.forward(self.x, dropout_mode=2 if self.dropout else 0)
+        ll, ld, lm = self.lambdas
+        e.loss(self.bbox, vertices=self.vertices if self.variant != "densebox" else None,
+               labels=self.labels if self.use_labels else None, rand_idx=self.rand,
+               lm_rand_idx=self.lm_rand if self.variant != "densebox" else None, lambda_loc=ll, lambda_det=ld,
+               lambda_lm=lm, global_pos_dev=self.gpos if self.world > 1 else None,
+               global_batch=self.B * self.world if self.world > 1 else -1, clamp_lm=self.use_labels)
+        e.backward()
+
+    def step(self, x, bbox, vertices=None, labels=None, rand_neg_idx=None, lm_rand_neg_idx=None):
+        """x [B,3,240,240] fp32 (host pinned or device), labels in 60-space. Returns the loss as a 0-dim CUDA tensor
+        (this rank's shard; call .item() to read it back)."""
+        e = self.eng
+        self._stage(self.x, x)
+        self._stage(self.bbox, bbox)
+        self._stage(self.vertices, vertices)
+        if labels is not None:
+            self._stage(self.labels, labels)
+            self.use_labels = True
+        if rand_neg_idx is None:
+            self.rand.copy_(torch.rand(self.B, 3600, device=self.device).argsort(dim=1)[:, :self.rand.shape[1]])
+        else:
+            r = torch.as_tensor(rand_neg_idx)
+            self.rand[:, :r.shape[1]].copy_(r[:, :self.rand.shape[1]], non_blocking=True)
+        if self.variant != "densebox":
+            if lm_rand_neg_idx is None:
+                self.lm_rand.copy_(torch.randint(0, 3600, (self.B, 4), device=self.device))
+            else:
+                self._stage(self.lm_rand, lm_rand_neg_idx)
+        if self.dropout:
+            drop = e.buffer("drop", torch.bfloat16)
+            check(lib().dbx_dropout_mask(ptr(drop), ctypes.c_ulonglong(drop.numel()), ctypes.c_ulonglong(self.seed),
+                                         ctypes.c_ulonglong(self.step_no * (drop.numel() // 8)), stream_ptr()),
+                  "dropout_mask")
+        if self.world > 1:
+            check(lib().dbx_count_positives(ptr(self.bbox), ptr(self.labels if self.use_labels else None),
+                                            c_int(self.B), ptr(self.gpos), stream_ptr()), "count_positives")
+            torch.distributed.all_reduce(self.gpos, group=self.pg)
+        graph_ok = self.use_graph and self.step_no >= 1  # step 0 runs eagerly (one-time inits, SGD first-step flag)
+        if graph_ok and self._graph_fb is None:
+            self._graph_fb = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph_fb):
+                self._fwd_loss_bwd()
+        if graph_ok:
+            self._graph_fb.replay()
+        else:
+            self._fwd_loss_bwd()
+        if self.world > 1:
+            torch.distributed.all_reduce(e.flat_grads(), group=self.pg)  # SUM: the loss is a sum over the batch
+        if graph_ok and (self._graph_sgd is None or self._graph_lr != self.lr):
+            self._graph_sgd = torch.cuda.CUDAGraph()
+            self._graph_lr = self.lr
+            with torch.cuda.graph(self._graph_sgd):
+                e.sgd_step(self.lr, self.momentum, self.weight_decay)
+            # capture does not execute: fall through to replay
+        if graph_ok:
+            self._graph_sgd.replay()
+        else:
+            e.sgd_step(self.lr, self.momentum, self.weight_decay)
+        self.step_no += 1
+        return e.loss_value()
+
+    def kernels_per_step(self):
+        """Number of this library's kernel launches in one training step (for bench.py's gpu_launches)."""
+        convs = 13 + (3 if self.variant != "densebox" else 0)          # fprop
+        fwd = 1 + convs + 3 + 1 + (2 if self.variant != "densebox" else 0)  # im2col, convs, pools, upsample, refine glue
+        dgrads = convs - 1
+        wgrads = convs * 2                                               # wgrad + bias colsum
+        bwd = dgrads + wgrads + 3 + 1 + 1 + (2 if self.variant != "densebox" else 0)
+        sgd = 1 + (convs - 1)
+        return fwd + 1 + bwd + sgd + (1 if self.dropout else 0) + (1 if self.world > 1 else 0)

@@ -33,6 +33,77 @@ int dbx_conv_fprop(const void* x, int N, int H, int W, int cin, int x_cs, int x_
 int dbx_conv_wgrad(const void* x, int N, int H, int W, int cin, int x_cs, int x_coff, const void* dy, int cout,
                    int dy_cs, int dy_coff, int R, int S, int pad, float* dw, int block_n, void* stream);
 
+/* The fused loss on caller-provided head maps (same semantics as dbx_net_loss below; used by the drop-in
+ * densebox_loss() op).  head: fp32 [B,60,60,HC] in the channel map below, rf: fp32 [B,60,60,RC] (variants 1,2).
+ * scratch: >= 16 + 4*B bytes of device memory, zeroed once before the first call.  Outputs may be NULL. */
+int dbx_loss_fwd_bwd(const float* head, int HC, const float* rf, int RC, const float* bbox, const float* vertices,
+                     const float* labels, const long long* rand_idx, int rand_stride, const long long* lm_rand_idx,
+                     int variant, float lambda_loc, float lambda_det, float lambda_lm, int global_pos,
+                     int global_batch, const int* global_pos_ptr, int clamp_lm, int B, void* scratch, float* loss,
+                     int* info, void* d_head_bf16, void* d_rf_bf16, float* d_head_f32, float* d_rf_f32,
+                     unsigned char* mask_out, unsigned char* lm_mask_out, void* stream);
+/* Positive pixels of a label shard (sum of the clipped init_score_map boxes, DenseBox.py:2864) -> *out (device). */
+int dbx_count_positives(const float* bbox, const float* labels, int B, int* out, void* stream);
+/* nn.Dropout(p=0.5) keep-mask x2 as bf16, Philox4x32-10 keyed by (seed, offset); n % 8 == 0. */
+int dbx_dropout_mask(void* mask, unsigned long long n, unsigned long long seed, unsigned long long offset,
+                     void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Network engine: one DenseBox replica (variant 0 = DenseBox :31-228, 1 = DenseBoxLM :232-473,
+ * 2 = DenseBoxLMLOC :477-738) for a fixed [N,3,H,W] input, laid out inside a caller-owned device workspace.
+ * The handle is a small host object; the engine never allocates device memory.
+ * Head-output channel map (head_out, fp32 [N,H/4,W/4,16|32]): 0 = score, 1..4 = bbox loc, 5..8 = landmark
+ * heat-maps, 9..16 = landmark offsets (variant 2);  rf_out (fp32 [N,H/4,W/4,16]): 0 = refine score. */
+#include <stddef.h>
+int dbx_net_workspace_bytes(int variant, int N, int H, int W, int train, size_t* bytes);
+int dbx_net_create(int variant, int N, int H, int W, int train, void* workspace, size_t bytes, void* stream,
+                   void** handle);
+int dbx_net_destroy(void* handle);
+/* Named region of the workspace ("head_out", "rf_out", "fusion", "drop", "d_head", "d_rf", "w32", "g32", ...). */
+int dbx_net_buffer(void* handle, const char* name, void** ptr, size_t* bytes);
+int dbx_net_head_channels(void* handle);
+long long dbx_net_param_elems(void* handle);
+
+/* state_dict plumbing (DenseBox.py:2809,2945): tensors are addressed by the reference's unique names
+ * ("conv1_1".."conv4_4" without conv3_3, "conv5_1_det", "conv5_2_loc", "conv6_1_det", ...); src/dst are fp32 device
+ * tensors [cout,cin,R,S] with the given element strides (bias: stride s_co only). */
+int dbx_net_set_param(void* handle, const char* name, int is_bias, const float* src, long s_co, long s_ci, long s_r,
+                      long s_s, void* stream);
+int dbx_net_get_param(void* handle, const char* name, int is_bias, float* dst, long s_co, long s_ci, long s_r,
+                      long s_s, void* stream);
+int dbx_net_get_grad(void* handle, const char* name, int is_bias, float* dst, long s_co, long s_ci, long s_r,
+                     long s_s, void* stream);
+/* Rebuild the flipped/transposed bf16 filters used by the data gradients (after set_param, before backward). */
+int dbx_net_refresh_dgrad(void* handle, void* stream);
+
+/* net.forward(X) — DenseBox.py:180-228 / :412-473 / :674-738. x: fp32 NCHW [N,3,H,W] device pointer.
+ * dropout_mode 0 = eval(), 1 = train() with a Philox mask drawn from (seed, offset), 2 = train() with the {0,2}
+ * bf16 mask the caller has written into the "drop" region (parity tests inject the oracle's mask). */
+int dbx_net_forward(void* handle, const float* x, int dropout_mode, unsigned long long seed,
+                    unsigned long long offset, void* stream);
+
+/* The loop body between forward and backward — DenseBox.py:2843-2918 (variant 0), :2575-2723 (1), :2300-2456 and
+ * :2023-2180 (2, `labels` != NULL selects the pos/neg-patch `_pn` helpers).  Inputs are device pointers:
+ * bbox [N,4] / vertices [N,8] in 60-space floats, labels [N] (or NULL), rand_idx [N,rand_stride] int64 = the
+ * np.random.choice draws (:2888-2893), lm_rand_idx [N,4] (:2676-2683).  global_pos/global_batch >= 0 give the
+ * batch-global positive count / size for data-parallel shards (:2864-2868); -1 = this launch is the whole batch;
+ * global_pos_ptr (device int, optional) overrides global_pos without a host sync (dbx_count_positives + allreduce).
+ * Writes the scalar loss to scalars[0] ("scalars" region, fp32), {half, pos} to scalars[2..3] (int32), the bf16
+ * head gradients into "d_head"/"d_rf" (train) and, when given, fp32 gradients [N,60,60,HC] / [N,60,60,16] and the
+ * selected masks (uint8 [N,3600] / [N,4,3600]). */
+int dbx_net_loss(void* handle, const float* bbox, const float* vertices, const float* labels,
+                 const long long* rand_idx, int rand_stride, const long long* lm_rand_idx, float lambda_loc,
+                 float lambda_det, float lambda_lm, int global_pos, int global_batch, const int* global_pos_ptr,
+                 int clamp_lm, float* d_head_f32, float* d_rf_f32, unsigned char* mask_out,
+                 unsigned char* lm_mask_out, void* stream);
+
+/* loss.backward() — DenseBox.py:2925: consumes "d_head"/"d_rf", accumulates (+=) parameter gradients into "g32". */
+int dbx_net_backward(void* handle, void* stream);
+int dbx_net_zero_grad(void* handle, void* stream);                       /* optimizer.zero_grad() :2858 */
+/* optimizer.step() — torch.optim.SGD(momentum, weight_decay) :2821-2824, :2926; also clears g32 and refreshes the
+ * bf16 filters. */
+int dbx_net_sgd_step(void* handle, float lr, float momentum, float weight_decay, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
