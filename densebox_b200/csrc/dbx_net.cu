@@ -9,6 +9,7 @@
 //   refine: rp[.,H/8,W/8,64] -> r1 -> r2 -> rup[N,H/4,W/4,64] -> rf_out fp32 [.,16]
 //   one gradient buffer per activation (d_*), parameters as flat fp32 master / grad / momentum + bf16 GEMM copies.
 #include "dbx_common.h"
+#include <stdio.h>
 #include <string.h>
 #include <string>
 #include <vector>
@@ -34,6 +35,10 @@ struct Param {  // one torch tensor pair (weight, bias) placed inside a group
 
 struct Buf { std::string name; size_t off, bytes; };
 
+#define DBX_TRY(expr) do { int _rc = (expr); if (_rc) return _rc; } while (0)
+#define DBX_K(tag, fl, expr) do { prof_begin(tag, fl, st); int _rc = (expr); prof_end(st); if (_rc) return _rc; } while (0)
+
+
 struct Net {
   int variant, N, H, W, train;
   int nh, HC;            // heads, head_out channels
@@ -47,6 +52,28 @@ struct Net {
   size_t wd_n = 0;       // bf16 elements in the dgrad-layout buffer
   bool forward_done = false, loss_done = false;
   int sgd_steps = 0;
+  // ---- per-launch accounting: every kernel launch of the engine goes through DBX_K (name, algorithmic FLOPs)
+  struct Rec { std::string tag; double flops; cudaEvent_t e0, e1; };
+  std::vector<Rec> recs;
+  bool profiling = false;
+  long long launches = 0;
+  void prof_begin(const char* tag, double flops, cudaStream_t st) {
+    ++launches;
+    if (!profiling) return;
+    Rec r; r.tag = tag; r.flops = flops;
+    cudaEventCreate(&r.e0); cudaEventCreate(&r.e1);
+    cudaEventRecord(r.e0, st);
+    recs.push_back(r);
+  }
+  void prof_end(cudaStream_t st) { if (profiling) cudaEventRecord(recs.back().e1, st); }
+  void prof_clear() { for (auto& r : recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); } recs.clear(); }
+  double macs_of(const char* grp) const {  // algorithmic (unpadded) multiply-adds per output pixel
+    const int gid = group_id(grp);
+    double m = 0;
+    for (auto& p : params) if (p.grp == gid) m += (double)p.cout * p.cin * p.R * p.S;
+    return m;
+  }
+  static double pixels(const Act& a) { return (double)a.N * a.H * a.W; }
 
   // ---- layout
   size_t cursor = 0;
@@ -238,8 +265,7 @@ struct Net {
   int refresh_dgrad(cudaStream_t st) {
     for (auto& g : groups) {
       if (!g.need_dgrad) continue;
-      int rc = transpose_dgrad(WK() + g.w_off, WD() + g.wd_off, g.rows, g.T, g.cin_pad, g.kpad, st);
-      if (rc) return rc;
+      DBX_K("transpose_dgrad", 0.0, transpose_dgrad(WK() + g.w_off, WD() + g.wd_off, g.rows, g.T, g.cin_pad, g.kpad, st));
     }
     return DBX_OK;
   }
@@ -250,20 +276,24 @@ struct Net {
     ConvEpilogue e;
     e.bias = bias_of(grp); e.relu = relu ? 1 : 0; e.aux = aux; e.aux_cs = aux_cs; e.aux_mode = aux_mode;
     e.out_fp32 = fp32 ? 1 : 0;
-    return conv_fprop(x, wk_of(grp), R, R, pad, out, e, block_n, st);
+    DBX_K((std::string("fprop:") + grp).c_str(), 2.0 * pixels(out) * macs_of(grp),
+          conv_fprop(x, wk_of(grp), R, R, pad, out, e, block_n, st));
+    return DBX_OK;
   }
   int dgrad(const Act& dy, const char* grp, int R, int pad, const Act& dx, const Act* relu_y, cudaStream_t st) {
     ConvEpilogue e;
     if (relu_y) { e.aux = relu_y->ptr; e.aux_cs = relu_y->cs; e.aux_coff = relu_y->coff; e.aux_mode = 1; }
-    return conv_fprop(dy, wd_of(grp), R, R, R - 1 - pad, dx, e, 0, st);
+    DBX_K((std::string("dgrad:") + grp).c_str(), 2.0 * pixels(dy) * macs_of(grp),
+          conv_fprop(dy, wd_of(grp), R, R, R - 1 - pad, dx, e, 0, st));
+    return DBX_OK;
   }
   int wgrad(const Act& x, const Act& dy, const char* grp, int R, int pad, cudaStream_t st) {
-    int rc = conv_wgrad(x, dy, R, R, pad, gw_of(grp), 0, st);
-    if (rc) return rc;
-    return colsum(dy, gb_of(grp), st);
+    DBX_K((std::string("wgrad:") + grp).c_str(), 2.0 * pixels(dy) * macs_of(grp),
+          conv_wgrad(x, dy, R, R, pad, gw_of(grp), 0, st));
+    DBX_K((std::string("colsum:") + grp).c_str(), 0.0, colsum(dy, gb_of(grp), st));
+    return DBX_OK;
   }
 
-#define DBX_TRY(expr) do { int _rc = (expr); if (_rc) return _rc; } while (0)
 
   // dropout_mode: 0 = eval (identity), 1 = draw a Philox mask (seed, offset), 2 = use the mask already in `drop`
   int forward(const float* x, int dropout_mode, unsigned long long seed, unsigned long long offset, cudaStream_t st) {
@@ -278,36 +308,36 @@ struct Net {
     Act p3 = act("p3", h8, w8, 256), a41 = act("a41", h8, w8, 512), a42 = act("a42", h8, w8, 512);
     Act a43 = act("a43", h8, w8, 512), a44 = act("a44", h8, w8, 512);
     Act hd = act("hd", h4, w4, 512 * nh), ho = act("head_out", h4, w4, HC);
-    DBX_TRY(im2col3x3_c3(x, col0.ptr, N, H, W, st));
+    DBX_K("im2col", 0.0, im2col3x3_c3(x, col0.ptr, N, H, W, st));
     DBX_TRY(conv(col0, "conv1_1", 1, 0, a11, true, nullptr, 0, 0, false, 0, st));
     DBX_TRY(conv(a11, "conv1_2", 3, 1, a12, true, nullptr, 0, 0, false, 0, st));
-    DBX_TRY(maxpool2x2_fwd(a12, p1, st));
+    DBX_K("pool_fwd", 0.0, maxpool2x2_fwd(a12, p1, st));
     DBX_TRY(conv(p1, "conv2_1", 3, 1, a21, true, nullptr, 0, 0, false, 0, st));
     DBX_TRY(conv(a21, "conv2_2", 3, 1, a22, true, nullptr, 0, 0, false, 0, st));
-    DBX_TRY(maxpool2x2_fwd(a22, p2, st));
+    DBX_K("pool_fwd", 0.0, maxpool2x2_fwd(a22, p2, st));
     DBX_TRY(conv(p2, "conv3_1", 3, 1, a31, true, nullptr, 0, 0, false, 0, st));
     DBX_TRY(conv(a31, "conv3_2", 3, 1, a32, true, nullptr, 0, 0, false, 0, st));
     DBX_TRY(conv(a32, "conv3_4", 3, 1, a34, true, nullptr, 0, 0, false, 0, st));  // conv3_3 skipped (:193-195)
-    DBX_TRY(maxpool2x2_fwd(a34, p3, st));
+    DBX_K("pool_fwd", 0.0, maxpool2x2_fwd(a34, p3, st));
     DBX_TRY(conv(p3, "conv4_1", 3, 1, a41, true, nullptr, 0, 0, false, 0, st));
     DBX_TRY(conv(a41, "conv4_2", 3, 1, a42, true, nullptr, 0, 0, false, 0, st));
     DBX_TRY(conv(a42, "conv4_3", 3, 1, a43, true, nullptr, 0, 0, false, 0, st));
     DBX_TRY(conv(a43, "conv4_4", 3, 1, a44, true, nullptr, 0, 0, false, 0, st));
-    DBX_TRY(upsample_bilinear_fwd(a44, fus_up, st));
+    DBX_K("upsample_fwd", 0.0, upsample_bilinear_fwd(a44, fus_up, st));
     const void* drop = nullptr;
     if (dropout_mode) {
       drop = buf("drop");
-      if (dropout_mode == 1) DBX_TRY(dropout_mask(buf("drop"), (size_t)N * h4 * w4 * 512 * nh, seed, offset, st));
+      if (dropout_mode == 1) DBX_K("dropout_mask", 0.0, dropout_mask(buf("drop"), (size_t)N * h4 * w4 * 512 * nh, seed, offset, st));
     }
     DBX_TRY(conv(fus, "heads1", 1, 0, hd, false, drop, 512 * nh, drop ? 2 : 0, false, 0, st));
     DBX_TRY(conv(hd, "heads2", 1, 0, ho, false, nullptr, 0, 0, true, 0, st));
     if (variant >= 1) {
       Act rp = act("rp", h8, w8, 64), r1 = act("r1", h8 - 2, w8 - 2, 64), r2 = act("r2", h8 - 6, w8 - 6, 64);
       Act rup = act("rup", h4, w4, 64), rf = act("rf_out", h4, w4, 16);
-      DBX_TRY(refine_pool_pack((const float*)ho.ptr, HC, rp.ptr, N, h4, w4, st));
+      DBX_K("refine_pool_pack", 0.0, refine_pool_pack((const float*)ho.ptr, HC, rp.ptr, N, h4, w4, st));
       DBX_TRY(conv(rp, "conv6_1_det", 3, 0, r1, false, nullptr, 0, 0, false, 0, st));
       DBX_TRY(conv(r1, "conv6_2_det", 5, 0, r2, false, nullptr, 0, 0, false, 0, st));
-      DBX_TRY(upsample_bilinear_fwd(r2, rup, st));
+      DBX_K("upsample_fwd", 0.0, upsample_bilinear_fwd(r2, rup, st));
       DBX_TRY(conv(rup, "conv6_3_det", 1, 0, rf, false, nullptr, 0, 0, true, 0, st));
     }
     dropout_used = dropout_mode != 0;
@@ -337,7 +367,7 @@ struct Net {
     p.d_head = train ? (__nv_bfloat16*)buf("d_head") : nullptr;
     p.d_rf = (train && variant >= 1) ? (__nv_bfloat16*)buf("d_rf") : nullptr;
     p.d_head_f32 = d_head_f32; p.d_rf_f32 = d_rf_f32; p.mask_out = mask_out; p.lm_mask_out = lm_mask_out;
-    DBX_TRY(loss_fwd_bwd(p, st));
+    DBX_K("loss", 0.0, loss_fwd_bwd(p, st));
     loss_done = true;
     return DBX_OK;
   }
@@ -370,26 +400,27 @@ struct Net {
       Act d_r1 = act("d_r1", h8 - 2, w8 - 2, 64), d_rp = act("d_rp", h8, w8, 64);
       DBX_TRY(wgrad(rup, d_rf16, "conv6_3_det", 1, 0, st));
       DBX_TRY(dgrad(d_rf64, "conv6_3_det", 1, 0, d_rup, nullptr, st));
-      DBX_TRY(upsample_bilinear_bwd(d_rup, nullptr, d_r2, st));
+      DBX_K("upsample_bwd", 0.0, upsample_bilinear_bwd(d_rup, nullptr, d_r2, st));
       DBX_TRY(wgrad(r1, d_r2, "conv6_2_det", 5, 0, st));
       DBX_TRY(dgrad(d_r2, "conv6_2_det", 5, 0, d_r1, nullptr, st));
       DBX_TRY(wgrad(rp, d_r1, "conv6_1_det", 3, 0, st));
       DBX_TRY(dgrad(d_r1, "conv6_1_det", 3, 0, d_rp, nullptr, st));
-      DBX_TRY(refine_pool_bwd((const float*)buf("head_out"), HC, d_rp.ptr, d_head64.ptr, N, h4, w4, st));
+      DBX_K("refine_pool_bwd", 0.0, refine_pool_bwd((const float*)buf("head_out"), HC, d_rp.ptr, d_head64.ptr, N, h4, w4, st));
     }
     // heads
     DBX_TRY(wgrad(hd, d_headC, "heads2", 1, 0, st));
     {
       const Group& g = groups[group_id("heads2")];
-      DBX_TRY(blockdiag_mask(G32() + g.w_off, g.rows, g.ld, nh, ch_start, st));
+      DBX_K("blockdiag_mask", 0.0, blockdiag_mask(G32() + g.w_off, g.rows, g.ld, nh, ch_start, st));
       ConvEpilogue e;
       if (dropout_used) { e.aux = buf("drop"); e.aux_cs = 512 * nh; e.aux_mode = 2; }
-      DBX_TRY(conv_fprop(d_head64, wd_of("heads2"), 1, 1, 0, d_hd, e, 0, st));
+      DBX_K("dgrad:heads2", 2.0 * pixels(d_head64) * macs_of("heads2"),
+            conv_fprop(d_head64, wd_of("heads2"), 1, 1, 0, d_hd, e, 0, st));
     }
     DBX_TRY(wgrad(fus, d_hd, "heads1", 1, 0, st));
     DBX_TRY(dgrad(d_hd, "heads1", 1, 0, d_fus, nullptr, st));
     // conv4 block
-    DBX_TRY(upsample_bilinear_bwd(d_fus_up, &a44, d_a44, st));
+    DBX_K("upsample_bwd", 0.0, upsample_bilinear_bwd(d_fus_up, &a44, d_a44, st));
     DBX_TRY(wgrad(a43, d_a44, "conv4_4", 3, 1, st));
     DBX_TRY(dgrad(d_a44, "conv4_4", 3, 1, d_a43, &a43, st));
     DBX_TRY(wgrad(a42, d_a43, "conv4_3", 3, 1, st));
@@ -399,7 +430,7 @@ struct Net {
     DBX_TRY(wgrad(p3, d_a41, "conv4_1", 3, 1, st));
     DBX_TRY(dgrad(d_a41, "conv4_1", 3, 1, d_p3, nullptr, st));
     // conv3 block: pool3 backward + the concat branch of conv3_4, then ReLU mask
-    DBX_TRY(maxpool2x2_bwd(a34, d_p3, &d_fus_34, d_a34, st));
+    DBX_K("pool_bwd", 0.0, maxpool2x2_bwd(a34, d_p3, &d_fus_34, d_a34, st));
     DBX_TRY(wgrad(a32, d_a34, "conv3_4", 3, 1, st));
     DBX_TRY(dgrad(d_a34, "conv3_4", 3, 1, d_a32, &a32, st));
     DBX_TRY(wgrad(a31, d_a32, "conv3_2", 3, 1, st));
@@ -407,13 +438,13 @@ struct Net {
     DBX_TRY(wgrad(p2, d_a31, "conv3_1", 3, 1, st));
     DBX_TRY(dgrad(d_a31, "conv3_1", 3, 1, d_p2, nullptr, st));
     // conv2 block
-    DBX_TRY(maxpool2x2_bwd(a22, d_p2, nullptr, d_a22, st));
+    DBX_K("pool_bwd", 0.0, maxpool2x2_bwd(a22, d_p2, nullptr, d_a22, st));
     DBX_TRY(wgrad(a21, d_a22, "conv2_2", 3, 1, st));
     DBX_TRY(dgrad(d_a22, "conv2_2", 3, 1, d_a21, &a21, st));
     DBX_TRY(wgrad(p1, d_a21, "conv2_1", 3, 1, st));
     DBX_TRY(dgrad(d_a21, "conv2_1", 3, 1, d_p1, nullptr, st));
     // conv1 block
-    DBX_TRY(maxpool2x2_bwd(a12, d_p1, nullptr, d_a12, st));
+    DBX_K("pool_bwd", 0.0, maxpool2x2_bwd(a12, d_p1, nullptr, d_a12, st));
     DBX_TRY(wgrad(a11, d_a12, "conv1_2", 3, 1, st));
     DBX_TRY(dgrad(d_a12, "conv1_2", 3, 1, d_a11, &a11, st));
     DBX_TRY(wgrad(col0, d_a11, "conv1_1", 1, 0, st));
@@ -427,7 +458,7 @@ struct Net {
 
   int sgd(float lr, float momentum, float wd, cudaStream_t st) {
     if (!train) return DBX_ERR_STATE;
-    DBX_TRY(sgd_step(W32(), G32(), V32(), WK(), flat_n, lr, momentum, wd, sgd_steps == 0 ? 1 : 0, 1, st));
+    DBX_K("sgd", 0.0, sgd_step(W32(), G32(), V32(), WK(), flat_n, lr, momentum, wd, sgd_steps == 0 ? 1 : 0, 1, st));
     ++sgd_steps;
     return refresh_dgrad(st);
   }
@@ -520,6 +551,24 @@ int dbx_net_backward(void* handle, void* stream) {
 int dbx_net_zero_grad(void* handle, void* stream) {
   if (!handle) return DBX_ERR_ARG;
   return ((Net*)handle)->zero_grad((cudaStream_t)stream);
+}
+int dbx_net_profile(void* handle, int enable) {
+  if (!handle) return DBX_ERR_ARG;
+  Net* n = (Net*)handle;
+  n->prof_clear();
+  n->profiling = enable != 0;
+  return DBX_OK;
+}
+long long dbx_net_launch_count(void* handle) { return handle ? ((Net*)handle)->launches : -1; }
+int dbx_net_profile_count(void* handle) { return handle ? (int)((Net*)handle)->recs.size() : DBX_ERR_ARG; }
+int dbx_net_profile_get(void* handle, int i, char* tag, int tag_bytes, double* flops, float* ms) {
+  if (!handle || !tag || !flops || !ms) return DBX_ERR_ARG;
+  Net* n = (Net*)handle;
+  if (i < 0 || i >= (int)n->recs.size()) return DBX_ERR_ARG;
+  const Net::Rec& r = n->recs[i];
+  snprintf(tag, tag_bytes, "%s", r.tag.c_str());
+  *flops = r.flops;
+  return (int)cudaEventElapsedTime(ms, r.e0, r.e1);
 }
 int dbx_net_sgd_step(void* handle, float lr, float momentum, float weight_decay, void* stream) {
   if (!handle) return DBX_ERR_ARG;

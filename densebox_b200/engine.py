@@ -148,3 +148,24 @@ class NetEngine:
 
     def flat_params(self):
         return self.buffer("w32", torch.float32)
+
+    # ---- measurement aids
+    def profile(self, enable=True):
+        check(lib().dbx_net_profile(self.h, c_int(int(enable))), "net_profile")
+
+    def launch_count(self):
+        lib().dbx_net_launch_count.restype = ctypes.c_longlong
+        return int(lib().dbx_net_launch_count(self.h))
+
+    def profile_records(self):
+        """[(tag, algorithmic flops, ms)] of every launch since profile(True); synchronises the device."""
+        torch.cuda.synchronize(self.device)
+        L = lib()
+        out = []
+        tag = ctypes.create_string_buffer(96)
+        fl, ms = ctypes.c_double(0), ctypes.c_float(0)
+        for i in range(L.dbx_net_profile_count(self.h)):
+            check(L.dbx_net_profile_get(self.h, c_int(i), tag, c_int(96), ctypes.byref(fl), ctypes.byref(ms)),
+                  "net_profile_get")
+            out.append((tag.value.decode(), fl.value, ms.value))
+        return out

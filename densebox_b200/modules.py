@@ -23,8 +23,7 @@ class _NativeForward(torch.autograd.Function):
     """forward = engine.forward, backward = engine.backward; parameters are listed so autograd routes their grads."""
 
     @staticmethod
-    def forward(ctx, module, x, *params):
-        eng = module._engine(x)
+    def forward(ctx, module, eng, x, *params):
         module._sync_params(eng)
         mode = 0
         if module.training:
@@ -51,7 +50,7 @@ class _NativeForward(torch.autograd.Function):
             w, b = module._wb(name)
             gw, gb = eng.get_tensor(name, w, b, grad=True)
             grads += [gw, gb]
-        return (None, None) + tuple(grads)
+        return (None, None, None) + tuple(grads)
 
 
 class _DenseBoxBase(nn.Module):
@@ -147,7 +146,7 @@ class _DenseBoxBase(nn.Module):
         params = []
         for name in unique_param_names(self.variant):
             params += list(self._wb(name))
-        return _NativeForward.apply(self, X, *params)
+        return _NativeForward.apply(self, self._engine(X), X, *params)
 
 
 class DenseBox(_DenseBoxBase):

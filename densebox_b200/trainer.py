@@ -64,7 +64,7 @@ class DenseBoxTrainer:
 
     # ---- one step
     def _stage(self, dst, src):
-        if src is None:
+        if src is None or src is dst:
             return
         src = torch.as_tensor(src)
         dst.copy_(src.reshape(dst.shape) if src.numel() == dst.numel() else src, non_blocking=True)

@@ -104,6 +104,14 @@ int dbx_net_zero_grad(void* handle, void* stream);                       /* opti
  * bf16 filters. */
 int dbx_net_sgd_step(void* handle, float lr, float momentum, float weight_decay, void* stream);
 
+/* Measurement aids: per-launch CUDA-event timing of the engine's own kernels (eager mode; synchronise before
+ * reading) and the number of kernel launches issued so far.  tags: "fprop:<layer>", "dgrad:<layer>",
+ * "wgrad:<layer>", "pool_fwd", "loss", ...; flops = algorithmic (unpadded) FLOPs of that launch. */
+int dbx_net_profile(void* handle, int enable);
+long long dbx_net_launch_count(void* handle);
+int dbx_net_profile_count(void* handle);
+int dbx_net_profile_get(void* handle, int i, char* tag, int tag_bytes, double* flops, float* ms);
+
 #ifdef __cplusplus
 }
 #endif

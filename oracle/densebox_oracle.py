@@ -77,53 +77,76 @@ def params_from_state_dict(sd, variant):
     """Pick the unique tensors out of a reference state_dict (every backbone/head tensor appears under two names)."""
     P = {}
     for name, _ in BACKBONE:
-        P[name + ".weight"] = sd[name + "_1.weight"].detach().clone().float()
-        P[name + ".bias"] = sd[name + "_1.bias"].detach().clone().float()
+        P[name + ".weight"] = sd[name + "_1.weight"].detach().cpu().clone().float()
+        P[name + ".bias"] = sd[name + "_1.bias"].detach().cpu().clone().float()
     names = ["conv5_1_%s" % h for h, _ in HEADS[variant]] + ["conv5_2_%s" % h for h, _ in HEADS[variant]]
     if variant != "densebox":
         names += ["conv6_1_det", "conv6_2_det", "conv6_3_det"]
     for nm in names:
-        P[nm + ".weight"] = sd[nm + ".weight"].detach().clone().float()
-        P[nm + ".bias"] = sd[nm + ".bias"].detach().clone().float()
+        P[nm + ".weight"] = sd[nm + ".weight"].detach().cpu().clone().float()
+        P[nm + ".bias"] = sd[nm + ".bias"].detach().cpu().clone().float()
     return P
 
 
 # ------------------------------------------------------------------------------------------------ forward
-def _cr(x, P, name):
-    return F.relu(F.conv2d(x, P[name + ".weight"], P[name + ".bias"], padding=1))
+class _StoreBF16(torch.autograd.Function):
+    """Emulation of bf16 STORAGE of a tensor (not part of the reference): forward rounds the value (fwd=True),
+    backward rounds the gradient.  Lets the tests separate "the CUDA backward is implemented correctly" (tight match
+    against this emulation) from the inherent effect of bf16 activations on ReLU masks / pool arg-maxes."""
+
+    @staticmethod
+    def forward(ctx, x, fwd):
+        return x.bfloat16().float() if fwd else x.clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.bfloat16().float(), None
 
 
-def _head(fusion, P, head, drop):
+def _cr(x, P, name, st):
+    return st(F.relu(F.conv2d(x, P[name + ".weight"], P[name + ".bias"], padding=1)))
+
+
+def _head(fusion, P, head, drop, st):
     h = F.conv2d(fusion, P["conv5_1_%s.weight" % head], P["conv5_1_%s.bias" % head])
     if drop is not None:  # train mode: nn.Dropout(p=0.5) == multiply by a {0,2} mask (injected for parity)
         h = h * drop
-    return F.conv2d(h, P["conv5_2_%s.weight" % head], P["conv5_2_%s.bias" % head])
+    return F.conv2d(st(h), P["conv5_2_%s.weight" % head], P["conv5_2_%s.bias" % head])
 
 
-def forward(P, X, variant="densebox", dropout=None, return_intermediates=False):
-    """Reference forward.  dropout: None (eval) or {head: mask[B,512,h,w] of 0/2} (train)."""
-    x = _cr(X, P, "conv1_1"); x = _cr(x, P, "conv1_2"); x = F.max_pool2d(x, 2, 2)
-    x = _cr(x, P, "conv2_1"); x = _cr(x, P, "conv2_2"); x = F.max_pool2d(x, 2, 2)
-    x = _cr(x, P, "conv3_1"); x = _cr(x, P, "conv3_2"); c34 = _cr(x, P, "conv3_4")  # conv3_3 skipped (:193-195)
-    x = F.max_pool2d(c34, 2, 2)
-    x = _cr(x, P, "conv4_1"); x = _cr(x, P, "conv4_2"); x = _cr(x, P, "conv4_3"); c44 = _cr(x, P, "conv4_4")
-    up = F.interpolate(c44, size=(c34.shape[2], c34.shape[3]), mode="bilinear", align_corners=True)
-    fusion = torch.cat((up, c34), dim=1)  # upsampled conv4_4 first (:219)
+def forward(P, X, variant="densebox", dropout=None, return_intermediates=False, emulate_bf16_storage=False):
+    """Reference forward.  dropout: None (eval) or {head: mask[B,512,h,w] of 0/2} (train).
+    emulate_bf16_storage=True additionally rounds every stored activation (and its gradient) to bf16 at the points
+    where the CUDA engine stores bf16 — a test aid, see _StoreBF16; the reference itself is fp32 throughout."""
+    if emulate_bf16_storage:
+        st = lambda t: _StoreBF16.apply(t, True)      # value and gradient stored as bf16
+        gb = lambda t: _StoreBF16.apply(t, False)     # only the gradient is stored as bf16
+    else:
+        st = gb = lambda t: t
+    x = _cr(X, P, "conv1_1", st); x = _cr(x, P, "conv1_2", st); x = gb(F.max_pool2d(x, 2, 2))
+    x = _cr(x, P, "conv2_1", st); x = _cr(x, P, "conv2_2", st); x = gb(F.max_pool2d(x, 2, 2))
+    x = _cr(x, P, "conv3_1", st); x = _cr(x, P, "conv3_2", st)
+    c34 = _cr(x, P, "conv3_4", st)  # conv3_3 skipped (:193-195)
+    x = gb(F.max_pool2d(c34, 2, 2))
+    x = _cr(x, P, "conv4_1", st); x = _cr(x, P, "conv4_2", st); x = _cr(x, P, "conv4_3", st)
+    c44 = _cr(x, P, "conv4_4", st)
+    up = st(F.interpolate(c44, size=(c34.shape[2], c34.shape[3]), mode="bilinear", align_corners=True))
+    fusion = gb(torch.cat((up, c34), dim=1))  # upsampled conv4_4 first (:219)
     d = dropout or {}
-    score = _head(fusion, P, "det", d.get("det"))
-    loc = _head(fusion, P, "loc", d.get("loc"))
+    score = gb(_head(fusion, P, "det", d.get("det"), st))
+    loc = gb(_head(fusion, P, "loc", d.get("loc"), st))
     inter = {"conv3_4": c34, "conv4_4": c44, "fusion": fusion}
     if variant == "densebox":
         out = (score, loc)
     else:
-        lm = _head(fusion, P, "landmark", d.get("landmark"))
-        lmloc = _head(fusion, P, "lmloc", d.get("lmloc")) if variant == "lmloc" else None
+        lm = gb(_head(fusion, P, "landmark", d.get("landmark"), st))
+        lmloc = gb(_head(fusion, P, "lmloc", d.get("lmloc"), st)) if variant == "lmloc" else None
         x = torch.cat((lm, score), dim=1)
-        x = F.max_pool2d(x, 2, 2)
-        x = F.conv2d(x, P["conv6_1_det.weight"], P["conv6_1_det.bias"])
-        x = F.conv2d(x, P["conv6_2_det.weight"], P["conv6_2_det.bias"])
-        x = F.interpolate(x, size=(score.shape[2], score.shape[3]), mode="bilinear", align_corners=True)
-        rf = F.conv2d(x, P["conv6_3_det.weight"], P["conv6_3_det.bias"])
+        x = st(F.max_pool2d(x, 2, 2))
+        x = st(F.conv2d(x, P["conv6_1_det.weight"], P["conv6_1_det.bias"]))
+        x = st(F.conv2d(x, P["conv6_2_det.weight"], P["conv6_2_det.bias"]))
+        x = st(F.interpolate(x, size=(score.shape[2], score.shape[3]), mode="bilinear", align_corners=True))
+        rf = gb(F.conv2d(x, P["conv6_3_det.weight"], P["conv6_3_det.bias"]))
         out = (score, loc, lm, rf) if variant == "lm" else (score, rf, loc, lm, lmloc)  # return orders :473, :738
     return (out, inter) if return_intermediates else out
 
@@ -299,7 +322,8 @@ def loss(outs, variant, bbox, rand_idx, vertices=None, lm_rand_idx=None, labels=
     Lloc = (loc - t(gts["loc"])) ** 2
     cls_sum = torch.sum(m * Ls)
     loc_sum = torch.sum(m * g * Lloc)
-    info = {"half": half, "pos": pos, "mask": mask, "hard": hard, "cls_sum": float(cls_sum), "loc_sum": float(loc_sum)}
+    info = {"half": half, "pos": pos, "mask": mask, "hard": hard, "cls_sum": float(cls_sum.detach()),
+            "loc_sum": float(loc_sum.detach())}
     if variant == "densebox":
         total = cls_sum + torch.sum(lambda_loc * (m * g * Lloc))  # :2917-2918
         return total, info
