@@ -74,4 +74,34 @@ int dbx_dropout_mask(void* mask, unsigned long long n, unsigned long long seed, 
   return dropout_mask(mask, (size_t)n, seed, offset, (cudaStream_t)stream);
 }
 
+int dbx_im2col3x3_c3(const float* x, void* out, int N, int H, int W, void* stream) {
+  return im2col3x3_c3(x, out, N, H, W, (cudaStream_t)stream);
+}
+int dbx_maxpool2x2_fwd(const void* y, int N, int H, int W, int C, int y_cs, int y_coff, void* out, int o_cs, int o_coff,
+                       void* stream) {
+  return maxpool2x2_fwd(mk_act(y, N, H, W, C, y_cs, y_coff), mk_act(out, N, H / 2, W / 2, C, o_cs, o_coff),
+                        (cudaStream_t)stream);
+}
+int dbx_maxpool2x2_bwd(const void* y, int N, int H, int W, int C, int y_cs, int y_coff, const void* dp, int dp_cs,
+                       int dp_coff, const void* add, int add_cs, int add_coff, void* dy, int dy_cs, int dy_coff,
+                       void* stream) {
+  Act a = mk_act(add, N, H, W, C, add_cs, add_coff);
+  return maxpool2x2_bwd(mk_act(y, N, H, W, C, y_cs, y_coff), mk_act(dp, N, H / 2, W / 2, C, dp_cs, dp_coff),
+                        add ? &a : nullptr, mk_act(dy, N, H, W, C, dy_cs, dy_coff), (cudaStream_t)stream);
+}
+int dbx_upsample_bilinear_fwd(const void* in, int N, int h, int w, int C, int in_cs, int in_coff, void* out, int H,
+                              int W, int o_cs, int o_coff, void* stream) {
+  return upsample_bilinear_fwd(mk_act(in, N, h, w, C, in_cs, in_coff), mk_act(out, N, H, W, C, o_cs, o_coff),
+                               (cudaStream_t)stream);
+}
+int dbx_upsample_bilinear_bwd(const void* dout, int N, int H, int W, int C, int d_cs, int d_coff, const void* relu_y,
+                              int y_cs, int y_coff, void* din, int h, int w, int i_cs, int i_coff, void* stream) {
+  Act y = mk_act(relu_y, N, h, w, C, y_cs, y_coff);
+  return upsample_bilinear_bwd(mk_act(dout, N, H, W, C, d_cs, d_coff), relu_y ? &y : nullptr,
+                               mk_act(din, N, h, w, C, i_cs, i_coff), (cudaStream_t)stream);
+}
+int dbx_colsum(const void* dy, int N, int H, int W, int C, int cs, int coff, float* db, void* stream) {
+  return colsum(mk_act(dy, N, H, W, C, cs, coff), db, (cudaStream_t)stream);
+}
+
 }  // extern "C"

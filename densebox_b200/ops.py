@@ -66,3 +66,53 @@ def conv_wgrad(x, dy, R, S, pad, dw, block_n=0):
         stream_ptr())
     check(rc, "conv_wgrad")
     return dw
+
+
+def im2col3x3_c3(x, out):
+    N, _, H, W = x.shape
+    check(lib().dbx_im2col3x3_c3(ptr(x), ptr(out), c_int(N), c_int(H), c_int(W), stream_ptr()), "im2col3x3_c3")
+    return out
+
+
+def _vargs(v):
+    return [ptr(v.buf), c_int(v.cs), c_int(v.coff)]
+
+
+def maxpool2x2_fwd(y, out):
+    y, out = _v(y), _v(out)
+    check(lib().dbx_maxpool2x2_fwd(ptr(y.buf), c_int(y.N), c_int(y.H), c_int(y.W), c_int(y.C), c_int(y.cs),
+                                   c_int(y.coff), *_vargs(out), stream_ptr()), "maxpool2x2_fwd")
+    return out
+
+
+def maxpool2x2_bwd(y, dp, dy, add=None):
+    y, dp, dy = _v(y), _v(dp), _v(dy)
+    a = _vargs(_v(add)) if add is not None else [ptr(None), c_int(0), c_int(0)]
+    check(lib().dbx_maxpool2x2_bwd(ptr(y.buf), c_int(y.N), c_int(y.H), c_int(y.W), c_int(y.C), c_int(y.cs),
+                                   c_int(y.coff), *_vargs(dp), *a, *_vargs(dy), stream_ptr()), "maxpool2x2_bwd")
+    return dy
+
+
+def upsample_bilinear_fwd(x, out):
+    x, out = _v(x), _v(out)
+    check(lib().dbx_upsample_bilinear_fwd(ptr(x.buf), c_int(x.N), c_int(x.H), c_int(x.W), c_int(x.C), c_int(x.cs),
+                                          c_int(x.coff), ptr(out.buf), c_int(out.H), c_int(out.W), c_int(out.cs),
+                                          c_int(out.coff), stream_ptr()), "upsample_bilinear_fwd")
+    return out
+
+
+def upsample_bilinear_bwd(dout, din, relu_y=None):
+    dout, din = _v(dout), _v(din)
+    y = _vargs(_v(relu_y)) if relu_y is not None else [ptr(None), c_int(0), c_int(0)]
+    check(lib().dbx_upsample_bilinear_bwd(ptr(dout.buf), c_int(dout.N), c_int(dout.H), c_int(dout.W), c_int(dout.C),
+                                          c_int(dout.cs), c_int(dout.coff), *y, ptr(din.buf), c_int(din.H),
+                                          c_int(din.W), c_int(din.cs), c_int(din.coff), stream_ptr()),
+          "upsample_bilinear_bwd")
+    return din
+
+
+def colsum(dy, db):
+    dy = _v(dy)
+    check(lib().dbx_colsum(ptr(dy.buf), c_int(dy.N), c_int(dy.H), c_int(dy.W), c_int(dy.C), c_int(dy.cs),
+                           c_int(dy.coff), ptr(db), stream_ptr()), "colsum")
+    return db

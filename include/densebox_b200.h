@@ -33,6 +33,25 @@ int dbx_conv_fprop(const void* x, int N, int H, int W, int cin, int x_cs, int x_
 int dbx_conv_wgrad(const void* x, int N, int H, int W, int cin, int x_cs, int x_coff, const void* dy, int cout,
                    int dy_cs, int dy_coff, int R, int S, int pad, float* dw, int block_n, void* stream);
 
+/* HBM-bound neighbours of the convolutions (NHWC bf16 views, 8-channel vectors; C % 8 == 0):
+ *  im2col3x3_c3        : X fp32 NCHW [N,3,H,W] -> bf16 [N,H,W,64] (27 taps*channels + zero pad) feeding conv1_1 (:185)
+ *  maxpool2x2_fwd/bwd  : nn.MaxPool2d(2,2) (:187,:191,:204) and its backward fused with the ReLU mask of the
+ *                        producing conv and an optional second gradient (`add`, the concat branch of conv3_4)
+ *  upsample_bilinear_* : nn.Upsample(size, 'bilinear', align_corners=True) (:213-216,:468-470); bwd optionally
+ *                        applies the ReLU mask of `relu_y`
+ *  colsum              : db[c] += sum over pixels (bias gradient) */
+int dbx_im2col3x3_c3(const float* x, void* out, int N, int H, int W, void* stream);
+int dbx_maxpool2x2_fwd(const void* y, int N, int H, int W, int C, int y_cs, int y_coff, void* out, int o_cs, int o_coff,
+                       void* stream);
+int dbx_maxpool2x2_bwd(const void* y, int N, int H, int W, int C, int y_cs, int y_coff, const void* dp, int dp_cs,
+                       int dp_coff, const void* add, int add_cs, int add_coff, void* dy, int dy_cs, int dy_coff,
+                       void* stream);
+int dbx_upsample_bilinear_fwd(const void* in, int N, int h, int w, int C, int in_cs, int in_coff, void* out, int H,
+                              int W, int o_cs, int o_coff, void* stream);
+int dbx_upsample_bilinear_bwd(const void* dout, int N, int H, int W, int C, int d_cs, int d_coff, const void* relu_y,
+                              int y_cs, int y_coff, void* din, int h, int w, int i_cs, int i_coff, void* stream);
+int dbx_colsum(const void* dy, int N, int H, int W, int C, int cs, int coff, float* db, void* stream);
+
 /* The fused loss on caller-provided head maps (same semantics as dbx_net_loss below; used by the drop-in
  * densebox_loss() op).  head: fp32 [B,60,60,HC] in the channel map below, rf: fp32 [B,60,60,RC] (variants 1,2).
  * scratch: >= 16 + 4*B bytes of device memory, zeroed once before the first call.  Outputs may be NULL. */

@@ -347,12 +347,13 @@ def decode(score_map, loc_map, lmloc_map=None, K=10):
     dets = []
     for v, i in zip(vals.tolist(), idx.tolist()):
         xi, yi = i % w, i // w
-        l = [float(loc_map[0, c, yi, xi]) for c in range(4)]
-        row = [(xi - l[0]) * 4.0, (yi - l[1]) * 4.0, (xi - l[2]) * 4.0, (yi - l[3]) * 4.0, v]
+        # `xi - map[c, idx]` is a float32 tensor op in the reference; float(...) * 4.0 then runs in Python double
+        sub = lambda a, m, c: float(f32(a) - f32(float(m[0, c, yi, xi])))
+        row = [sub(xi, loc_map, 0) * 4.0, sub(yi, loc_map, 1) * 4.0, sub(xi, loc_map, 2) * 4.0,
+               sub(yi, loc_map, 3) * 4.0, v]
         if lmloc_map is not None:
             for k in range(4):
-                row += [(xi - float(lmloc_map[0, 2 * k, yi, xi])) * 4.0,
-                        (yi - float(lmloc_map[0, 2 * k + 1, yi, xi])) * 4.0]
+                row += [sub(xi, lmloc_map, 2 * k) * 4.0, sub(yi, lmloc_map, 2 * k + 1) * 4.0]
         dets.append(row)
     return np.asarray(dets, dtype=np.float64)
 
