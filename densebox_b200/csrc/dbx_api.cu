@@ -75,7 +75,7 @@ int dbx_dropout_mask(void* mask, unsigned long long n, unsigned long long seed, 
 }
 
 int dbx_im2col3x3_c3(const float* x, void* out, int N, int H, int W, void* stream) {
-  return im2col3x3_c3(x, out, N, H, W, (cudaStream_t)stream);
+  return im2col3x3_c3(x, out, N, H, W, 1, (cudaStream_t)stream);
 }
 int dbx_maxpool2x2_fwd(const void* y, int N, int H, int W, int C, int y_cs, int y_coff, void* out, int o_cs, int o_coff,
                        void* stream) {
@@ -102,6 +102,13 @@ int dbx_upsample_bilinear_bwd(const void* dout, int N, int H, int W, int C, int 
 }
 int dbx_colsum(const void* dy, int N, int H, int W, int C, int cs, int coff, float* db, void* stream) {
   return colsum(mk_act(dy, N, H, W, C, cs, coff), db, (cudaStream_t)stream);
+}
+
+int dbx_decode_nms(const float* score, long s_img, long s_pix, const float* loc, long l_img, long l_pix, long l_ch,
+                   const float* lmloc, long m_img, long m_pix, long m_ch, int N, int H4, int W4, int K, double thresh,
+                   float* dets, int* keep, void* stream) {
+  return decode_nms(score, s_img, s_pix, loc, l_img, l_pix, l_ch, lmloc, m_img, m_pix, m_ch, N, H4, W4, K, thresh,
+                    dets, keep, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -64,7 +64,7 @@ int conv_wgrad(const Act& x, const Act& dy, int R, int S, int pad, float* dw, in
 
 
 // ---- HBM-bound kernels (dbx_elementwise.cu)
-int im2col3x3_c3(const float* x, void* out, int N, int H, int W, cudaStream_t st);
+int im2col3x3_c3(const float* x, void* out, int N, int H, int W, int write_pad, cudaStream_t st);
 int maxpool2x2_fwd(const Act& y, const Act& o, cudaStream_t st);
 int maxpool2x2_bwd(const Act& y, const Act& dp, const Act* add, const Act& dy, cudaStream_t st);
 int upsample_bilinear_fwd(const Act& in, const Act& out, cudaStream_t st);
@@ -112,5 +112,11 @@ struct LossParams {
 };
 int loss_fwd_bwd(const LossParams& p, cudaStream_t st);
 int count_positives(const float* bbox, const float* labels, int B, int* out, cudaStream_t st);
+
+
+// ---- detection post-processing (dbx_postproc.cu); maps are fp32 with explicit image/pixel/channel element strides
+int decode_nms(const float* score, long s_img, long s_pix, const float* loc, long l_img, long l_pix, long l_ch,
+               const float* lmloc, long m_img, long m_pix, long m_ch, int N, int H4, int W4, int K, double thresh,
+               float* dets, int* keep, cudaStream_t st);
 
 }  // namespace dbx

@@ -25,32 +25,41 @@ __device__ __forceinline__ bf16* at(const Act& a, int n, int y, int x, int c) {
 // ------------------------------------------------------------------------------------------------ ingest
 // X fp32 NCHW [N,3,H,W] -> bf16 [N,H,W,64]: channel (r*3+s)*3+c holds X[n,c,y+r-1,x+s-1] (zero outside), channels
 // 27..63 are zero.  conv1_1 (DenseBox.py:185) then is a K=64 1x1 GEMM on the tensor cores.
-__global__ void im2col3x3_c3_kernel(const float* __restrict__ x, bf16* __restrict__ out, int N, int H, int W) {
-  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const size_t total = (size_t)N * H * W * 8;
-  if (idx >= total) return;
-  const int chunk = (int)(idx & 7);
-  const size_t pix = idx >> 3;
+__global__ void im2col3x3_c3_kernel(const float* __restrict__ x, bf16* __restrict__ out, int N, int H, int W,
+                                    int write_pad) {
+  const size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= (size_t)N * H * W) return;
   const int xw = (int)(pix % W), y = (int)((pix / W) % H), n = (int)(pix / ((size_t)W * H));
-  float f[8];
+  float f[32];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int k = chunk * 8 + j;
-    float v = 0.f;
-    if (k < 27) {
-      const int tap = k / 3, c = k - tap * 3, r = tap / 3, s = tap - r * 3;
-      const int yy = y + r - 1, xx = xw + s - 1;
-      if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = __ldg(x + (((size_t)n * 3 + c) * H + yy) * W + xx);
+  for (int k = 27; k < 32; ++k) f[k] = 0.f;
+  const float* xn = x + (size_t)n * 3 * H * W;
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const int yy = y + r - 1;
+    const bool yok = yy >= 0 && yy < H;
+#pragma unroll
+    for (int s = 0; s < 3; ++s) {
+      const int xx = xw + s - 1;
+      const bool ok = yok && xx >= 0 && xx < W;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) f[(r * 3 + s) * 3 + c] = ok ? __ldg(xn + ((size_t)c * H + yy) * W + xx) : 0.f;
     }
-    f[j] = v;
   }
-  reinterpret_cast<uint4*>(out)[idx] = pack8(f);
+  uint4* o = reinterpret_cast<uint4*>(out + pix * 64);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) o[q] = pack8(f + 8 * q);
+  if (write_pad) {
+#pragma unroll
+    for (int q = 4; q < 8; ++q) o[q] = make_uint4(0u, 0u, 0u, 0u);
+  }
 }
 
-int im2col3x3_c3(const float* x, void* out, int N, int H, int W, cudaStream_t st) {
+// write_pad = 0: channels 32..63 are left untouched (the engine zeroes them once at creation).
+int im2col3x3_c3(const float* x, void* out, int N, int H, int W, int write_pad, cudaStream_t st) {
   if (!x || !out) return DBX_ERR_ARG;
-  const size_t total = (size_t)N * H * W * 8;
-  im2col3x3_c3_kernel<<<grid_for(total, 256), 256, 0, st>>>(x, (bf16*)out, N, H, W);
+  const size_t total = (size_t)N * H * W;
+  im2col3x3_c3_kernel<<<grid_for(total, 128), 128, 0, st>>>(x, (bf16*)out, N, H, W, write_pad);
   return (int)cudaGetLastError();
 }
 
@@ -240,7 +249,20 @@ __global__ void colsum_kernel(Act dy, float* __restrict__ db, int rows, size_t p
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[j] = 0.f;
   const bf16* base = reinterpret_cast<const bf16*>(dy.ptr) + dy.coff + chunk * 8;
-  for (size_t p = p0 + r; p < p1; p += rows) {
+  size_t p = p0 + r;
+  for (; p + 3 * (size_t)rows < p1; p += 4 * (size_t)rows) {
+    uint4 u[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) u[q] = ldg16(base + (p + q * (size_t)rows) * dy.cs);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float f[8];
+      unpack8(u[q], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += f[j];
+    }
+  }
+  for (; p < p1; p += rows) {
     float f[8];
     unpack8(ldg16(base + p * dy.cs), f);
 #pragma unroll
@@ -261,7 +283,7 @@ int colsum(const Act& dy, float* db, cudaStream_t st) {
   const int cc = dy.C / 8;
   int rows = 256 / cc; if (rows < 1) rows = 1;
   const size_t pixels = (size_t)dy.N * dy.H * dy.W;
-  int blocks = 4 * num_sms();
+  int blocks = 8 * num_sms();
   if ((size_t)blocks * rows > pixels) blocks = (int)((pixels + rows - 1) / rows);
   if (blocks < 1) blocks = 1;
   const size_t ppb = (pixels + blocks - 1) / blocks;

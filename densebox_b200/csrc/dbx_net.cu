@@ -308,7 +308,7 @@ struct Net {
     Act p3 = act("p3", h8, w8, 256), a41 = act("a41", h8, w8, 512), a42 = act("a42", h8, w8, 512);
     Act a43 = act("a43", h8, w8, 512), a44 = act("a44", h8, w8, 512);
     Act hd = act("hd", h4, w4, 512 * nh), ho = act("head_out", h4, w4, HC);
-    DBX_K("im2col", 0.0, im2col3x3_c3(x, col0.ptr, N, H, W, st));
+    DBX_K("im2col", 0.0, im2col3x3_c3(x, col0.ptr, N, H, W, 0, st));
     DBX_TRY(conv(col0, "conv1_1", 1, 0, a11, true, nullptr, 0, 0, false, 0, st));
     DBX_TRY(conv(a11, "conv1_2", 3, 1, a12, true, nullptr, 0, 0, false, 0, st));
     DBX_K("pool_fwd", 0.0, maxpool2x2_fwd(a12, p1, st));

@@ -1,0 +1,97 @@
+// densebox_b200 — detection post-processing, one CTA per image: top-K of the raw score map, box / landmark decode
+// and greedy NMS (reference: parse_out_MN / parse_DetLMLOC DenseBox.py:3114-3217, NMS :3398-3443).
+// The reference does this on the CPU after five D2H copies per image; here only K rows leave the GPU.
+#include "dbx_common.h"
+#include "dbx_ptx.cuh"
+
+namespace dbx {
+
+static constexpr int PT = 1024, KMAX = 64;
+
+struct MapView { const float* p; long img, pix, ch; };  // element strides: image, pixel, channel
+__device__ __forceinline__ float mv(const MapView& m, int n, int idx, int c) {
+  return __ldg(m.p + (size_t)n * m.img + (size_t)idx * m.pix + (size_t)c * m.ch);
+}
+
+__global__ void __launch_bounds__(PT) decode_nms_kernel(MapView score, MapView loc, MapView lmloc, int has_lm, int HW,
+                                                        int W4, int K, double thresh, float* __restrict__ dets,
+                                                        int* __restrict__ keep) {
+  __shared__ float wv[PT / 32];
+  __shared__ int wi[PT / 32];
+  __shared__ int sel[KMAX];
+  __shared__ float selv[KMAX];
+  __shared__ double box[KMAX][4];
+  __shared__ int alive[KMAX];
+  const int n = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int KS = K;  // row stride of the outputs
+  if (K > KMAX) K = KMAX;
+  if (K > HW) K = HW;
+  // ---- top-K by K rounds of block arg-max (ties: lowest index); torch.topk(sorted) order = descending score
+  for (int k = 0; k < K; ++k) {
+    float bv = -INFINITY; int bi = 0x7fffffff;
+    for (int i = tid; i < HW; i += PT) {
+      bool taken = false;
+      for (int j = 0; j < k; ++j) taken |= (sel[j] == i);
+      if (taken) continue;
+      const float v = mv(score, n, i, 0);
+      if (v > bv || (v == bv && i < bi) || bi == 0x7fffffff) { bv = v; bi = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (oi != 0x7fffffff && (bi == 0x7fffffff || ov > bv || (ov == bv && oi < bi))) { bv = ov; bi = oi; }
+    }
+    if (lane == 0) { wv[warp] = bv; wi[warp] = bi; }
+    __syncthreads();
+    if (tid == 0) {
+      float v = wv[0]; int i = wi[0];
+      for (int w = 1; w < PT / 32; ++w)
+        if (wi[w] != 0x7fffffff && (i == 0x7fffffff || wv[w] > v || (wv[w] == v && wi[w] < i))) { v = wv[w]; i = wi[w]; }
+      sel[k] = i; selv[k] = v;
+    }
+    __syncthreads();
+  }
+  // ---- decode (:3162-3213): float32 `xi - map[idx]`, then * 4.0
+  if (tid < K) {
+    const int idx = sel[tid], xi = idx % W4, yi = idx / W4;
+    float* d = dets + ((size_t)n * KS + tid) * 13;
+    float b[4];
+    for (int c = 0; c < 4; ++c) b[c] = __fsub_rn((float)((c & 1) ? yi : xi), mv(loc, n, idx, c)) * 4.0f;
+    d[0] = b[0]; d[1] = b[1]; d[2] = b[2]; d[3] = b[3]; d[4] = selv[tid];
+    for (int c = 0; c < 8; ++c)
+      d[5 + c] = has_lm ? __fsub_rn((float)((c & 1) ? yi : xi), mv(lmloc, n, idx, c)) * 4.0f : 0.f;
+    for (int c = 0; c < 4; ++c) box[tid][c] = (double)b[c];
+    alive[tid] = 1;
+  }
+  __syncthreads();
+  // ---- greedy NMS (:3406-3441): rows are already in descending score order
+  if (tid == 0) {
+    for (int i = 0; i < K; ++i) {
+      keep[(size_t)n * KS + i] = alive[i];
+      if (!alive[i]) continue;
+      const double ai = (box[i][2] - box[i][0] + 1) * (box[i][3] - box[i][1] + 1);
+      for (int j = i + 1; j < K; ++j) {
+        if (!alive[j]) continue;
+        const double xx1 = fmax(box[i][0], box[j][0]), yy1 = fmax(box[i][1], box[j][1]);
+        const double xx2 = fmin(box[i][2], box[j][2]), yy2 = fmin(box[i][3], box[j][3]);
+        const double w = fmax(0.0, xx2 - xx1 + 1), h = fmax(0.0, yy2 - yy1 + 1);
+        const double inter = w * h;
+        const double aj = (box[j][2] - box[j][0] + 1) * (box[j][3] - box[j][1] + 1);
+        const double ovr = inter / (ai + aj - inter);
+        if (!(ovr <= thresh)) alive[j] = 0;
+      }
+    }
+  }
+}
+
+int decode_nms(const float* score, long s_img, long s_pix, const float* loc, long l_img, long l_pix, long l_ch,
+               const float* lmloc, long m_img, long m_pix, long m_ch, int N, int H4, int W4, int K, double thresh,
+               float* dets, int* keep, cudaStream_t st) {
+  if (!score || !loc || !dets || !keep || N <= 0 || K <= 0 || K > KMAX) return DBX_ERR_ARG;
+  MapView s{score, s_img, s_pix, 0}, l{loc, l_img, l_pix, l_ch}, m{lmloc ? lmloc : loc, m_img, m_pix, m_ch};
+  decode_nms_kernel<<<N, PT, 0, st>>>(s, l, m, lmloc ? 1 : 0, H4 * W4, W4, K, thresh, dets, keep);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace dbx

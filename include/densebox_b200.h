@@ -52,6 +52,15 @@ int dbx_upsample_bilinear_bwd(const void* dout, int N, int H, int W, int C, int 
                               int y_cs, int y_coff, void* din, int h, int w, int i_cs, int i_coff, void* stream);
 int dbx_colsum(const void* dy, int N, int H, int W, int C, int cs, int coff, float* db, void* stream);
 
+/* Detection post-processing — parse_out_MN / parse_DetLM / parse_DetLMLOC (DenseBox.py:3114-3348) + NMS (:3398-3443),
+ * one CTA per image: top-K of the raw score map (no sigmoid / threshold, as in the reference), decode
+ * x = (xi - loc[c, idx]) * 4, greedy NMS (areas with +1, keep while IoU <= thresh).  Maps are fp32 with explicit
+ * element strides (image, pixel, channel) so NCHW tensors and the engine's NHWC buffers both work.
+ * dets: [N,K,13] fp32 rows (xt,yt,xb,yb,score,x0,y0..x3,y3) in descending score order; keep: [N,K] int32 flags. */
+int dbx_decode_nms(const float* score, long s_img, long s_pix, const float* loc, long l_img, long l_pix, long l_ch,
+                   const float* lmloc, long m_img, long m_pix, long m_ch, int N, int H4, int W4, int K, double thresh,
+                   float* dets, int* keep, void* stream);
+
 /* The fused loss on caller-provided head maps (same semantics as dbx_net_loss below; used by the drop-in
  * densebox_loss() op).  head: fp32 [B,60,60,HC] in the channel map below, rf: fp32 [B,60,60,RC] (variants 1,2).
  * scratch: >= 16 + 4*B bytes of device memory, zeroed once before the first call.  Outputs may be NULL. */
