@@ -51,6 +51,7 @@ struct ConvEpilogue {
   int aux_cs = 0, aux_coff = 0;
   int aux_mode = 0;            // 0 none, 1 out = aux>0 ? v : 0 (ReLU backward), 2 out = v*aux (dropout scale)
   int out_fp32 = 0;            // output element type: 0 bf16, 1 fp32
+  int epi_bufs = 0;            // 0 = auto; 2/4/8 epilogue staging boxes (short-K GEMMs with a mask want a deep ring)
 };
 
 // out[n,oh,ow,:] = epi( sum_{r,s,ci} x[n,oh+r-pad,ow+s-pad,ci] * wk[co][(r*S+s)*Cin+ci] )

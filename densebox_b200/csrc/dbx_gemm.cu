@@ -18,9 +18,11 @@
 
 namespace dbx {
 
-static constexpr int kThreads = 192;
+static constexpr int kThreads = 192;          // wgrad: 1 TMA + 1 MMA + 4 epilogue warps
+static constexpr int kFpropThreads = 320;     // fprop: 1 TMA + 1 MMA + 8 epilogue warps (2 per TMEM lane quarter)
 static constexpr int kMaxStages = 8;
-static constexpr int kSmemBudget = 220 * 1024;
+static constexpr int kSmemBudget = 230400;      // usable dynamic smem (227 KB - alignment slack - static barriers)
+static constexpr int kEpiBuf = 16384;           // one epilogue staging buffer: 128 rows x 64 bf16 channels
 
 // ------------------------------------------------------------------------------------------------ host helpers
 int num_sms() {
@@ -127,13 +129,15 @@ struct FpropParams {
   int aux_cs, aux_coff, aux_mode;
   void* out;
   int out_cs, out_coff, out_fp32;
+  int tma_epi, nbuf, nsb;  // bf16 outputs: epilogue staged through `nbuf` smem buffers, `nsb` 64-column blocks/tile
 };
 
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kFpropThreads, 1)
 conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmX,
                   const FpropParams p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t full_bar[kMaxStages], empty_bar[kMaxStages], tfull_bar[2], tempty_bar[2];
+  __shared__ uint64_t full_bar[kMaxStages], empty_bar[kMaxStages], tfull_bar[2], tempty_bar[2], aux_bar[8];
   __shared__ uint32_t tmem_base_s;
 
   const uint32_t raw = smem_u32(smem_raw);
@@ -149,7 +153,9 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 4); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 8); }
+    for (int b = 0; b < 8; ++b) mbar_init(&aux_bar[b], 1);
+    if (p.tma_epi) { tma_prefetch_desc(&tmO); if (p.aux_mode) tma_prefetch_desc(&tmX); }
     fence_barrier_init();
   }
   if (warp == 1) { tmem_alloc(&tmem_base_s, p.tmem_cols); tmem_relinquish(); }
@@ -207,74 +213,177 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else {
     // ===================== epilogue (warps 2..5 -> TMEM lane quarters 2,3,0,1) =====================
-    const int q = warp & 3;
-    const int row = q * 32 + lane;
-    const int box_rows = p.tw * p.th * p.tn;
-    int it = 0;
-    for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
-      const int buf = it & 1; const uint32_t use = (uint32_t)(it >> 1);
-      const int nt = t / p.m_tiles, mt = t % p.m_tiles;
-      const int w = (mt % p.tiles_w) * p.tw + row % p.tw;
-      const int h = ((mt / p.tiles_w) % p.tiles_h) * p.th + (row / p.tw) % p.th;
-      const int n = (mt / (p.tiles_w * p.tiles_h)) * p.tn + row / (p.tw * p.th);
-      const bool valid = row < box_rows && w < p.out_W && h < p.out_H && n < p.out_N;
-      const size_t pix = ((size_t)n * p.out_H + h) * p.out_W + w;
-      mbar_wait(&tfull_bar[buf], use & 1);
-      tc_fence_after();
-      const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * p.block_n);
-      for (int c0 = 0; c0 < p.block_n; c0 += 16) {
-        uint32_t v[16];
-        tmem_ld_x16(taddr + c0, v);
-        tmem_ld_wait();
-        const int ch = nt * p.block_n + c0;
-        if (valid && ch < p.cout) {
-          float f[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
-          if (p.bias) {
-            const float4* bp = reinterpret_cast<const float4*>(p.bias + ch);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              float4 b4 = __ldg(bp + j);
-              f[4 * j] += b4.x; f[4 * j + 1] += b4.y; f[4 * j + 2] += b4.z; f[4 * j + 3] += b4.w;
-            }
+    if (p.tma_epi) {
+      // bf16 outputs: TMEM -> registers -> (bias, ReLU, mask) -> swizzled smem box -> TMA store.  The mask tile is
+      // TMA-loaded into the same box two 64-column blocks ahead and transformed in place, so no epilogue thread
+      // ever waits on a global load and every global access of the kernel is a bulk tensor copy.
+      const int q4 = warp & 3, half = (warp - 2) >> 2;  // TMEM lane quarter, 32-column half of each 64-column block
+      const int row = q4 * 32 + lane;
+      const bool leader = threadIdx.x == 64;
+      const int box_rows = p.tw * p.th * p.tn;
+      const uint32_t box_bytes = (uint32_t)box_rows * 128u;
+      uint8_t* ring = smem + (size_t)p.stages * stage_bytes;
+      const int nsb = p.nsb, nbuf = p.nbuf, D = p.nbuf >> 1;
+      const int my_tiles = (int)blockIdx.x < total ? (total - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+      const int total_sb = my_tiles * nsb;
+      auto issue_aux = [&](int qq) {
+        const int t2 = blockIdx.x + (qq / nsb) * gridDim.x, j2 = qq % nsb;
+        const int nt2 = t2 / p.m_tiles, mt2 = t2 % p.m_tiles;
+        const int b2 = qq % nbuf;
+        mbar_arrive_expect_tx(&aux_bar[b2], box_bytes);
+        tma_load_4d(&tmX, &aux_bar[b2], ring + (size_t)b2 * kEpiBuf, nt2 * p.block_n + j2 * 64,
+                    (mt2 % p.tiles_w) * p.tw, ((mt2 / p.tiles_w) % p.tiles_h) * p.th,
+                    (mt2 / (p.tiles_w * p.tiles_h)) * p.tn);
+      };
+      if (leader && p.aux_mode)
+        for (int q0 = 0; q0 < D && q0 < total_sb; ++q0) issue_aux(q0);
+      int it = 0, q = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+        const int buf = it & 1; const uint32_t use = (uint32_t)(it >> 1);
+        const int nt = t / p.m_tiles, mt = t % p.m_tiles;
+        const int w0 = (mt % p.tiles_w) * p.tw, h0 = ((mt / p.tiles_w) % p.tiles_h) * p.th;
+        const int n0 = (mt / (p.tiles_w * p.tiles_h)) * p.tn;
+        mbar_wait(&tfull_bar[buf], use & 1);
+        tc_fence_after();
+        const uint32_t taddr = tmem + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(buf * p.block_n);
+        for (int j = 0; j < nsb; ++j, ++q) {
+          if (leader) {
+            // the box that is re-filled next (aux prefetch D blocks ahead) must be drained: nbuf - D - 1 stores may pend
+            if (nbuf == 8) bulk_wait_read<3>(); else if (nbuf == 4) bulk_wait_read<1>(); else bulk_wait_read<0>();
+            if (p.aux_mode && q + D < total_sb) issue_aux(q + D);
           }
-          if (p.relu) {
+          named_bar_sync(1, 256);
+          uint8_t* sb = ring + (size_t)(q % nbuf) * kEpiBuf;
+          if (p.aux_mode) mbar_wait(&aux_bar[q % nbuf], (uint32_t)((q / nbuf) & 1));
+          int ncols = p.block_n - j * 64; if (ncols > 64) ncols = 64;
+          int cend = half * 32 + 32; if (cend > ncols) cend = ncols;
+          for (int c0 = half * 32; c0 < cend; c0 += 16) {
+            uint32_t v[16];
+            tmem_ld_x16(taddr + j * 64 + c0, v);
+            tmem_ld_wait();
+            const int ch = nt * p.block_n + j * 64 + c0;
+            if (row < box_rows) {
+              float f[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
-          }
-          if (p.aux_mode) {
-            const uint4* ap = reinterpret_cast<const uint4*>(p.aux + pix * p.aux_cs + p.aux_coff + ch);
-            uint4 a0 = __ldg(ap), a1 = __ldg(ap + 1);
-            uint32_t au[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+              for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
+              if (p.bias && ch < p.cout) {
+                const float4* bp = reinterpret_cast<const float4*>(p.bias + ch);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float lo = bf16lo(au[j]), hi = bf16hi(au[j]);
-              if (p.aux_mode == 1) {
-                f[2 * j] = lo > 0.f ? f[2 * j] : 0.f;
-                f[2 * j + 1] = hi > 0.f ? f[2 * j + 1] : 0.f;
-              } else {
-                f[2 * j] *= lo;
-                f[2 * j + 1] *= hi;
+                for (int i = 0; i < 4; ++i) {
+                  const float4 b4 = __ldg(bp + i);
+                  f[4 * i] += b4.x; f[4 * i + 1] += b4.y; f[4 * i + 2] += b4.z; f[4 * i + 3] += b4.w;
+                }
               }
+              if (p.relu) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
+              }
+              const int cc = c0 >> 3;
+              uint4* s0 = reinterpret_cast<uint4*>(sb + row * 128 + (((cc) ^ (row & 7)) << 4));
+              uint4* s1 = reinterpret_cast<uint4*>(sb + row * 128 + (((cc + 1) ^ (row & 7)) << 4));
+              if (p.aux_mode) {
+                const uint4 a0 = *s0, a1 = *s1;
+                const uint32_t au[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const float lo = bf16lo(au[i]), hi = bf16hi(au[i]);
+                  if (p.aux_mode == 1) {
+                    f[2 * i] = lo > 0.f ? f[2 * i] : 0.f;
+                    f[2 * i + 1] = hi > 0.f ? f[2 * i + 1] : 0.f;
+                  } else {
+                    f[2 * i] *= lo;
+                    f[2 * i + 1] *= hi;
+                  }
+                }
+              }
+              *s0 = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
+                               pack_bf16x2(f[6], f[7]));
+              *s1 = make_uint4(pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]), pack_bf16x2(f[12], f[13]),
+                               pack_bf16x2(f[14], f[15]));
             }
           }
-          if (p.out_fp32) {
-            float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + pix * p.out_cs + p.out_coff + ch);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-          } else {
-            uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + pix * p.out_cs + p.out_coff + ch);
-            op[0] = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
-                               pack_bf16x2(f[6], f[7]));
-            op[1] = make_uint4(pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]), pack_bf16x2(f[12], f[13]),
-                               pack_bf16x2(f[14], f[15]));
+          fence_proxy_async_smem();
+          named_bar_sync(2, 256);
+          if (leader) {
+            tma_store_4d(&tmO, sb, nt * p.block_n + j * 64, w0, h0, n0);
+            bulk_commit();
           }
         }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[buf]);
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+      if (leader) bulk_wait_all();
+    } else {
+      const int q = warp & 3, half = (warp - 2) >> 2;
+      const int row = q * 32 + lane;
+      const int box_rows = p.tw * p.th * p.tn;
+      int it = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+        const int buf = it & 1; const uint32_t use = (uint32_t)(it >> 1);
+        const int nt = t / p.m_tiles, mt = t % p.m_tiles;
+        const int w = (mt % p.tiles_w) * p.tw + row % p.tw;
+        const int h = ((mt / p.tiles_w) % p.tiles_h) * p.th + (row / p.tw) % p.th;
+        const int n = (mt / (p.tiles_w * p.tiles_h)) * p.tn + row / (p.tw * p.th);
+        const bool valid = row < box_rows && w < p.out_W && h < p.out_H && n < p.out_N;
+        const size_t pix = ((size_t)n * p.out_H + h) * p.out_W + w;
+        mbar_wait(&tfull_bar[buf], use & 1);
+        tc_fence_after();
+        const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * p.block_n);
+        for (int c0 = half * 16; c0 < p.block_n; c0 += 32) {
+          uint32_t v[16];
+          tmem_ld_x16(taddr + c0, v);
+          tmem_ld_wait();
+          const int ch = nt * p.block_n + c0;
+          if (valid && ch < p.cout) {
+            float f[16];
+  #pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+            if (p.bias) {
+              const float4* bp = reinterpret_cast<const float4*>(p.bias + ch);
+  #pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float4 b4 = __ldg(bp + j);
+                f[4 * j] += b4.x; f[4 * j + 1] += b4.y; f[4 * j + 2] += b4.z; f[4 * j + 3] += b4.w;
+              }
+            }
+            if (p.relu) {
+  #pragma unroll
+              for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+            }
+            if (p.aux_mode) {
+              const uint4* ap = reinterpret_cast<const uint4*>(p.aux + pix * p.aux_cs + p.aux_coff + ch);
+              uint4 a0 = __ldg(ap), a1 = __ldg(ap + 1);
+              uint32_t au[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+  #pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                float lo = bf16lo(au[j]), hi = bf16hi(au[j]);
+                if (p.aux_mode == 1) {
+                  f[2 * j] = lo > 0.f ? f[2 * j] : 0.f;
+                  f[2 * j + 1] = hi > 0.f ? f[2 * j + 1] : 0.f;
+                } else {
+                  f[2 * j] *= lo;
+                  f[2 * j + 1] *= hi;
+                }
+              }
+            }
+            if (p.out_fp32) {
+              float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + pix * p.out_cs + p.out_coff + ch);
+  #pragma unroll
+              for (int j = 0; j < 4; ++j) op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+            } else {
+              uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + pix * p.out_cs + p.out_coff + ch);
+              op[0] = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
+                                 pack_bf16x2(f[6], f[7]));
+              op[1] = make_uint4(pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]), pack_bf16x2(f[12], f[13]),
+                                 pack_bf16x2(f[14], f[15]));
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+      }
     }
   }
   tc_fence_before();
@@ -283,7 +392,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 }
 
 static int set_max_smem(const void* fn) {
-  cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget + 2048);
+  cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget + 1024);
   return (int)e;
 }
 
@@ -299,11 +408,27 @@ int conv_fprop(const Act& x, const void* wk, int R, int S, int pad, const Act& o
   if (block_n % 16 || block_n > 256 || block_n < 16) return DBX_ERR_ARG;
 
   Tile t = choose_tile(out.W, out.H, out.N, false);
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmO, tmX;
   int rc = encode_act_map(&tmA, x, t);
   if (rc) return rc;
   rc = encode_mat_map(&tmB, wk, out.C, R * S * x.C, block_n);
   if (rc) return rc;
+  const int tma_epi = epi.out_fp32 ? 0 : 1;
+  if (tma_epi) {
+    rc = encode_act_map(&tmO, out, t);
+    if (rc) return rc;
+    if (epi.aux_mode) {
+      Act ax = out;
+      ax.ptr = const_cast<void*>(epi.aux); ax.cs = epi.aux_cs; ax.coff = epi.aux_coff;
+      rc = encode_act_map(&tmX, ax, t);
+      if (rc) return rc;
+    } else {
+      tmX = tmO;
+    }
+  } else {
+    if (epi.aux_mode) return DBX_ERR_ARG;  // fp32 outputs (tiny head GEMMs) take no mask
+    tmO = tmA; tmX = tmA;
+  }
 
   FpropParams p{};
   p.tw = t.tw; p.th = t.th; p.tn = t.tn; p.tiles_w = t.tiles_w; p.tiles_h = t.tiles_h; p.tiles_n = t.tiles_n;
@@ -313,7 +438,13 @@ int conv_fprop(const Act& x, const void* wk, int R, int S, int pad, const Act& o
   p.m_tiles = t.count(); p.n_tiles = (out.C + block_n - 1) / block_n; p.block_n = block_n;
   p.cout = out.C;
   const int stage_bytes = 16384 + block_n * 128;
-  p.stages = kSmemBudget / stage_bytes;
+  p.tma_epi = tma_epi;
+  p.nsb = (block_n + 63) / 64;
+  p.nbuf = 4;
+  if (tma_epi && (kSmemBudget - 4 * kEpiBuf) / stage_bytes < 4) p.nbuf = 2;  // keep >= 4 operand stages for N = 256
+  if (tma_epi && (epi.epi_bufs == 2 || epi.epi_bufs == 4 || epi.epi_bufs == 8)) p.nbuf = epi.epi_bufs;
+  const int ring = tma_epi ? p.nbuf * kEpiBuf : 0;
+  p.stages = (kSmemBudget - ring) / stage_bytes;
   if (p.stages > kMaxStages) p.stages = kMaxStages;
   if (p.stages < 2) return DBX_ERR_ARG;
   p.idesc = umma_idesc_bf16(128, block_n, 0, 0);
@@ -326,8 +457,8 @@ int conv_fprop(const Act& x, const void* wk, int R, int S, int pad, const Act& o
   if (attr_rc) return attr_rc;
   const int total = p.m_tiles * p.n_tiles;
   const int grid = total < num_sms() ? total : num_sms();
-  const size_t smem = (size_t)p.stages * stage_bytes + 1024;
-  conv_fprop_kernel<<<grid, kThreads, smem, stream>>>(tmA, tmB, p);
+  const size_t smem = (size_t)p.stages * stage_bytes + ring + 1024;
+  conv_fprop_kernel<<<grid, kFpropThreads, smem, stream>>>(tmA, tmB, tmO, tmX, p);
   return (int)cudaGetLastError();
 }
 

@@ -276,6 +276,7 @@ struct Net {
     ConvEpilogue e;
     e.bias = bias_of(grp); e.relu = relu ? 1 : 0; e.aux = aux; e.aux_cs = aux_cs; e.aux_mode = aux_mode;
     e.out_fp32 = fp32 ? 1 : 0;
+    if (aux_mode && x.C * R * R <= 1024) e.epi_bufs = 4;  // short K with a mask (heads1): 3 stages + 4 boxes
     DBX_K((std::string("fprop:") + grp).c_str(), 2.0 * pixels(out) * macs_of(grp),
           conv_fprop(x, wk_of(grp), R, R, pad, out, e, block_n, st));
     return DBX_OK;
@@ -414,6 +415,7 @@ struct Net {
       DBX_K("blockdiag_mask", 0.0, blockdiag_mask(G32() + g.w_off, g.rows, g.ld, nh, ch_start, st));
       ConvEpilogue e;
       if (dropout_used) { e.aux = buf("drop"); e.aux_cs = 512 * nh; e.aux_mode = 2; }
+      e.epi_bufs = 8;  // K = 64: the kernel is its epilogue, prefetch the mask 4 blocks ahead
       DBX_K("dgrad:heads2", 2.0 * pixels(d_head64) * macs_of("heads2"),
             conv_fprop(d_head64, wd_of("heads2"), 1, 1, 0, d_hd, e, 0, st));
     }
