@@ -15,6 +15,7 @@
 #include "dbx_common.h"
 #include "dbx_ptx.cuh"
 #include <mutex>
+#include <stdlib.h>
 
 namespace dbx {
 
@@ -129,9 +130,11 @@ struct FpropParams {
   int aux_cs, aux_coff, aux_mode;
   void* out;
   int out_cs, out_coff, out_fp32;
+  int cta2;                // 1: CTA pairs drive tcgen05.mma.cta_group::2 (launched with cluster size 2)
   int tma_epi, nbuf, nsb;  // bf16 outputs: epilogue staged through `nbuf` smem buffers, `nsb` 64-column blocks/tile
 };
 
+template <bool kCta2>
 __global__ void __launch_bounds__(kFpropThreads, 1)
 conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmX,
@@ -143,24 +146,37 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // cta2: a pair of CTAs (one cluster, one TPC) works on two M-tiles with ONE tcgen05.mma.cta_group::2 per K step;
+  // each CTA stages its own A tile and HALF of the B tile, which halves the weight traffic per SM.
+  constexpr bool cta2 = kCta2;  // separate instantiations: a kernel holding cta_group::2 PTX must run in pairs
+  uint32_t rank = 0u;
+  if constexpr (cta2) rank = cluster_ctarank();
+  const int u0 = cta2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;      // first work unit of this CTA (pair)
+  const int ustep = cta2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int m_units = cta2 ? (p.m_tiles + 1) >> 1 : p.m_tiles;        // odd tail: the extra tile is fully out of bounds
+  const int total = m_units * p.n_tiles;
   const uint32_t a_bytes = (uint32_t)(p.tw * p.th * p.tn) * 128u;
-  const uint32_t b_bytes = (uint32_t)p.block_n * 128u;
+  const uint32_t b_rows = cta2 ? (uint32_t)p.block_n >> 1 : (uint32_t)p.block_n;
+  const uint32_t b_bytes = b_rows * 128u;
   const uint32_t stage_bytes = 16384u + b_bytes;
-  const int total = p.m_tiles * p.n_tiles;
   const int num_kb = p.R * p.S * p.cin_blocks;
+#define DBX_UNIT_TILE(u, nt, mt) const int nt = (u) / m_units, mt = cta2 ? 2 * ((u) % m_units) + (int)rank : (u) % m_units
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 8); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], cta2 ? 16 : 8); }
     for (int b = 0; b < 8; ++b) mbar_init(&aux_bar[b], 1);
     if (p.tma_epi) { tma_prefetch_desc(&tmO); if (p.aux_mode) tma_prefetch_desc(&tmX); }
     fence_barrier_init();
   }
-  if (warp == 1) { tmem_alloc(&tmem_base_s, p.tmem_cols); tmem_relinquish(); }
+  if (warp == 1) {
+    if constexpr (cta2) { tmem_alloc_2sm(&tmem_base_s, p.tmem_cols); tmem_relinquish_2sm(); }
+    else { tmem_alloc(&tmem_base_s, p.tmem_cols); tmem_relinquish(); }
+  }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (cta2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
 
@@ -168,8 +184,8 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int t = blockIdx.x; t < total; t += gridDim.x) {
-        const int nt = t / p.m_tiles, mt = t % p.m_tiles;
+      for (int u = u0; u < total; u += ustep) {
+        DBX_UNIT_TILE(u, nt, mt);
         const int w0 = (mt % p.tiles_w) * p.tw;
         const int h0 = ((mt / p.tiles_w) % p.tiles_h) * p.th;
         const int n0 = (mt / (p.tiles_w * p.tiles_h)) * p.tn;
@@ -178,18 +194,26 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             for (int cb = 0; cb < p.cin_blocks; ++cb) {
               mbar_wait(&empty_bar[stage], phase ^ 1);
               uint8_t* sa = smem + (size_t)stage * stage_bytes;
-              mbar_arrive_expect_tx(&full_bar[stage], a_bytes + b_bytes);
-              tma_load_4d(&tmA, &full_bar[stage], sa, cb * 64, w0 + s - p.pad, h0 + r - p.pad, n0);
-              tma_load_2d(&tmB, &full_bar[stage], sa + 16384, (r * p.S + s) * p.cin + cb * 64, nt * p.block_n);
+              const int kcol = (r * p.S + s) * p.cin + cb * 64;
+              if constexpr (cta2) {
+                // both CTAs' bytes land on the leader's barrier; only the leader arms it
+                if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2u * (a_bytes + b_bytes));
+                tma_load_4d_2sm(&tmA, &full_bar[stage], sa, cb * 64, w0 + s - p.pad, h0 + r - p.pad, n0);
+                tma_load_2d_2sm(&tmB, &full_bar[stage], sa + 16384, kcol, nt * p.block_n + (int)(rank * b_rows));
+              } else {
+                mbar_arrive_expect_tx(&full_bar[stage], a_bytes + b_bytes);
+                tma_load_4d(&tmA, &full_bar[stage], sa, cb * 64, w0 + s - p.pad, h0 + r - p.pad, n0);
+                tma_load_2d(&tmB, &full_bar[stage], sa + 16384, kcol, nt * p.block_n);
+              }
               if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    if (lane == 0 && rank == 0) {
       int stage = 0; uint32_t phase = 0; int it = 0;
-      for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+      for (int u = u0; u < total; u += ustep, ++it) {
         const int buf = it & 1; const uint32_t use = (uint32_t)(it >> 1);
         mbar_wait(&tempty_bar[buf], (use & 1) ^ 1);
         tc_fence_after();
@@ -203,12 +227,13 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           for (int k = 0; k < 4; ++k) {
             const uint64_t da = umma_smem_desc_sw128(a_addr + k * 32, 16, 1024);
             const uint64_t db = umma_smem_desc_sw128(b_addr + k * 32, 16, 1024);
-            umma_bf16(d_tmem, da, db, p.idesc, (uint32_t)((kb | k) != 0));
+            if constexpr (cta2) umma_bf16_2sm(d_tmem, da, db, p.idesc, (uint32_t)((kb | k) != 0));
+            else umma_bf16(d_tmem, da, db, p.idesc, (uint32_t)((kb | k) != 0));
           }
-          umma_commit(&empty_bar[stage]);
+          if constexpr (cta2) umma_commit_2sm(&empty_bar[stage], 3); else umma_commit(&empty_bar[stage]);
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull_bar[buf]);
+        if constexpr (cta2) umma_commit_2sm(&tfull_bar[buf], 3); else umma_commit(&tfull_bar[buf]);
       }
     }
   } else {
@@ -224,11 +249,11 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const uint32_t box_bytes = (uint32_t)box_rows * 128u;
       uint8_t* ring = smem + (size_t)p.stages * stage_bytes;
       const int nsb = p.nsb, nbuf = p.nbuf, D = p.nbuf >> 1;
-      const int my_tiles = (int)blockIdx.x < total ? (total - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+      const int my_tiles = u0 < total ? (total - 1 - u0) / ustep + 1 : 0;
       const int total_sb = my_tiles * nsb;
       auto issue_aux = [&](int qq) {
-        const int t2 = blockIdx.x + (qq / nsb) * gridDim.x, j2 = qq % nsb;
-        const int nt2 = t2 / p.m_tiles, mt2 = t2 % p.m_tiles;
+        const int u2 = u0 + (qq / nsb) * ustep, j2 = qq % nsb;
+        DBX_UNIT_TILE(u2, nt2, mt2);
         const int b2 = qq % nbuf;
         mbar_arrive_expect_tx(&aux_bar[b2], box_bytes);
         tma_load_4d(&tmX, &aux_bar[b2], ring + (size_t)b2 * kEpiBuf, nt2 * p.block_n + j2 * 64,
@@ -238,9 +263,9 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       if (leader && p.aux_mode)
         for (int q0 = 0; q0 < D && q0 < total_sb; ++q0) issue_aux(q0);
       int it = 0, q = 0;
-      for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+      for (int u = u0; u < total; u += ustep, ++it) {
         const int buf = it & 1; const uint32_t use = (uint32_t)(it >> 1);
-        const int nt = t / p.m_tiles, mt = t % p.m_tiles;
+        DBX_UNIT_TILE(u, nt, mt);
         const int w0 = (mt % p.tiles_w) * p.tw, h0 = ((mt / p.tiles_w) % p.tiles_h) * p.th;
         const int n0 = (mt / (p.tiles_w * p.tiles_h)) * p.tn;
         mbar_wait(&tfull_bar[buf], use & 1);
@@ -311,7 +336,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+        if (lane == 0) { if constexpr (cta2) mbar_arrive_cluster(&tempty_bar[buf], 0); else mbar_arrive(&tempty_bar[buf]); }
       }
       if (leader) bulk_wait_all();
     } else {
@@ -319,9 +344,9 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int row = q * 32 + lane;
       const int box_rows = p.tw * p.th * p.tn;
       int it = 0;
-      for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+      for (int u = u0; u < total; u += ustep, ++it) {
         const int buf = it & 1; const uint32_t use = (uint32_t)(it >> 1);
-        const int nt = t / p.m_tiles, mt = t % p.m_tiles;
+        DBX_UNIT_TILE(u, nt, mt);
         const int w = (mt % p.tiles_w) * p.tw + row % p.tw;
         const int h = ((mt / p.tiles_w) % p.tiles_h) * p.th + (row / p.tw) % p.th;
         const int n = (mt / (p.tiles_w * p.tiles_h)) * p.tn + row / (p.tw * p.th);
@@ -382,13 +407,18 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+        if (lane == 0) { if constexpr (cta2) mbar_arrive_cluster(&tempty_bar[buf], 0); else mbar_arrive(&tempty_bar[buf]); }
       }
     }
   }
   tc_fence_before();
-  __syncthreads();
-  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem, p.tmem_cols); }
+  __syncwarp();
+  if constexpr (cta2) cluster_sync_all(); else __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    if constexpr (cta2) tmem_dealloc_2sm(tmem, p.tmem_cols); else tmem_dealloc(tmem, p.tmem_cols);
+  }
+#undef DBX_UNIT_TILE
 }
 
 static int set_max_smem(const void* fn) {
@@ -408,12 +438,18 @@ int conv_fprop(const Act& x, const void* wk, int R, int S, int pad, const Act& o
   if (block_n % 16 || block_n > 256 || block_n < 16) return DBX_ERR_ARG;
 
   Tile t = choose_tile(out.W, out.H, out.N, false);
+  const int tma_epi = epi.out_fp32 ? 0 : 1;
+  // CTA pairs (tcgen05.mma.cta_group::2) whenever the B tile is worth halving
+  // (measured round 1: no gain over single CTAs on this path — the big layers are bound by wave quantisation and
+  // MMA issue, not by operand traffic — so pairing is opt-in: ConvEpilogue::force_cta2 = 1 or DBX_CTA2=1)
+  const bool cta2_ok = tma_epi && block_n >= 128 && block_n % 32 == 0 && t.count() >= 2 && num_sms() >= 2;
+  int cta2 = (cta2_ok && epi.force_cta2 == 1) ? 1 : 0;
+  { const char* e = getenv("DBX_CTA2"); if (e && cta2_ok) cta2 = e[0] == '1'; }  // A/B switch for measurements
   CUtensorMap tmA, tmB, tmO, tmX;
   int rc = encode_act_map(&tmA, x, t);
   if (rc) return rc;
-  rc = encode_mat_map(&tmB, wk, out.C, R * S * x.C, block_n);
+  rc = encode_mat_map(&tmB, wk, out.C, R * S * x.C, cta2 ? block_n / 2 : block_n);
   if (rc) return rc;
-  const int tma_epi = epi.out_fp32 ? 0 : 1;
   if (tma_epi) {
     rc = encode_act_map(&tmO, out, t);
     if (rc) return rc;
@@ -437,29 +473,47 @@ int conv_fprop(const Act& x, const void* wk, int R, int S, int pad, const Act& o
   p.cin = x.C; p.cin_blocks = x.C / 64;
   p.m_tiles = t.count(); p.n_tiles = (out.C + block_n - 1) / block_n; p.block_n = block_n;
   p.cout = out.C;
-  const int stage_bytes = 16384 + block_n * 128;
+  p.cta2 = cta2;
+  const int stage_bytes = 16384 + (cta2 ? block_n / 2 : block_n) * 128;
   p.tma_epi = tma_epi;
   p.nsb = (block_n + 63) / 64;
   p.nbuf = 4;
-  if (tma_epi && (kSmemBudget - 4 * kEpiBuf) / stage_bytes < 4) p.nbuf = 2;  // keep >= 4 operand stages for N = 256
+  if (tma_epi && (kSmemBudget - 4 * kEpiBuf) / stage_bytes < 4) p.nbuf = 2;  // keep >= 4 operand stages
   if (tma_epi && (epi.epi_bufs == 2 || epi.epi_bufs == 4 || epi.epi_bufs == 8)) p.nbuf = epi.epi_bufs;
   const int ring = tma_epi ? p.nbuf * kEpiBuf : 0;
   p.stages = (kSmemBudget - ring) / stage_bytes;
   if (p.stages > kMaxStages) p.stages = kMaxStages;
   if (p.stages < 2) return DBX_ERR_ARG;
-  p.idesc = umma_idesc_bf16(128, block_n, 0, 0);
+  p.idesc = umma_idesc_bf16(cta2 ? 256 : 128, block_n, 0, 0);
   p.tmem_cols = tmem_cols_for(2 * block_n);
   p.bias = epi.bias; p.relu = epi.relu;
   p.aux = (const bf16*)epi.aux; p.aux_cs = epi.aux_cs; p.aux_coff = epi.aux_coff; p.aux_mode = epi.aux_mode;
   p.out = out.ptr; p.out_cs = out.cs; p.out_coff = out.coff; p.out_fp32 = epi.out_fp32;
 
-  static int attr_rc = set_max_smem((const void*)conv_fprop_kernel);
-  if (attr_rc) return attr_rc;
-  const int total = p.m_tiles * p.n_tiles;
-  const int grid = total < num_sms() ? total : num_sms();
+  static int attr_rc1 = set_max_smem((const void*)conv_fprop_kernel<false>);
+  static int attr_rc2 = set_max_smem((const void*)conv_fprop_kernel<true>);
+  if (attr_rc1 || attr_rc2) return attr_rc1 ? attr_rc1 : attr_rc2;
   const size_t smem = (size_t)p.stages * stage_bytes + ring + 1024;
-  conv_fprop_kernel<<<grid, kFpropThreads, smem, stream>>>(tmA, tmB, tmO, tmX, p);
-  return (int)cudaGetLastError();
+  cudaLaunchConfig_t cfg{};
+  cfg.blockDim = dim3(kFpropThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  int grid;
+  if (cta2) {
+    const int units = ((p.m_tiles + 1) / 2) * p.n_tiles;
+    const int pairs = num_sms() / 2;
+    grid = 2 * (units < pairs ? units : pairs);
+  } else {
+    const int total = p.m_tiles * p.n_tiles;
+    grid = total < num_sms() ? total : num_sms();
+  }
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cta2 ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cfg.gridDim = dim3(grid);
+  if (cta2) return (int)cudaLaunchKernelEx(&cfg, conv_fprop_kernel<true>, tmA, tmB, tmO, tmX, p);
+  return (int)cudaLaunchKernelEx(&cfg, conv_fprop_kernel<false>, tmA, tmB, tmO, tmX, p);
 }
 
 // ------------------------------------------------------------------------------------------------ wgrad kernel
