@@ -60,6 +60,9 @@ struct ConvEpilogue {
 int conv_fprop(const Act& x, const void* wk, int R, int S, int pad, const Act& out, const ConvEpilogue& epi,
                int block_n, cudaStream_t stream);
 
+// 3x3 pad-1 convolution for Cin <= 128 with column-box reuse (dbx_conv_halo.cu); DBX_ERR_ARG = shape not handled.
+int conv3x3_halo(const Act& x, const void* wk, const Act& out, const ConvEpilogue& epi, cudaStream_t stream);
+
 // dw[co][(r*S+s)*Cin+ci] += sum_{n,oh,ow} dy[n,oh,ow,co] * x[n,oh+r-pad,ow+s-pad,ci]   (fp32, red.add)
 // dw has row stride R*S*x.C; rows = dy.C.
 int conv_wgrad(const Act& x, const Act& dy, int R, int S, int pad, float* dw, int block_n, cudaStream_t stream);

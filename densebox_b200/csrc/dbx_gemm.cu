@@ -180,60 +180,74 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
 
+  // Shared-window addresses are computed once: the hot loops below must stay a few dozen instructions per K block,
+  // a single warp issues them back to back (round 1 profile: the old MMA loop spent ~650 cycles/K-block on address
+  // arithmetic and per-instruction election loops and was the bottleneck of EVERY layer).
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
+  const uint32_t tfull0 = smem_u32(&tfull_bar[0]), tempty0 = smem_u32(&tempty_bar[0]);
+
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      for (int u = u0; u < total; u += ustep) {
-        DBX_UNIT_TILE(u, nt, mt);
-        const int w0 = (mt % p.tiles_w) * p.tw;
-        const int h0 = ((mt / p.tiles_w) % p.tiles_h) * p.th;
-        const int n0 = (mt / (p.tiles_w * p.tiles_h)) * p.tn;
-        for (int r = 0; r < p.R; ++r)
-          for (int s = 0; s < p.S; ++s)
-            for (int cb = 0; cb < p.cin_blocks; ++cb) {
-              mbar_wait(&empty_bar[stage], phase ^ 1);
-              uint8_t* sa = smem + (size_t)stage * stage_bytes;
-              const int kcol = (r * p.S + s) * p.cin + cb * 64;
+    // ===================== TMA producer (whole warp walks the schedule, one elected lane issues) ===============
+    int stage = 0; uint32_t phase = 0;
+    for (int u = u0; u < total; u += ustep) {
+      DBX_UNIT_TILE(u, nt, mt);
+      const int w0 = (mt % p.tiles_w) * p.tw - p.pad;
+      const int h0 = ((mt / p.tiles_w) % p.tiles_h) * p.th - p.pad;
+      const int n0 = (mt / (p.tiles_w * p.tiles_h)) * p.tn;
+      const int brow = nt * p.block_n + (int)(rank * b_rows) * (cta2 ? 1 : 0);
+      int kcol = 0;
+      for (int r = 0; r < p.R; ++r)
+        for (int s = 0; s < p.S; ++s)
+          for (int cb = 0; cb < p.cin_blocks; ++cb, kcol += 64) {
+            mbar_wait_a(empty0 + 8u * stage, phase ^ 1);
+            if (elect_one_sync()) {
+              const uint32_t sa = smem_base + (uint32_t)stage * stage_bytes, fb = full0 + 8u * stage;
               if constexpr (cta2) {
                 // both CTAs' bytes land on the leader's barrier; only the leader arms it
-                if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2u * (a_bytes + b_bytes));
-                tma_load_4d_2sm(&tmA, &full_bar[stage], sa, cb * 64, w0 + s - p.pad, h0 + r - p.pad, n0);
-                tma_load_2d_2sm(&tmB, &full_bar[stage], sa + 16384, kcol, nt * p.block_n + (int)(rank * b_rows));
+                if (rank == 0) mbar_arrive_expect_tx_a(fb, 2u * (a_bytes + b_bytes));
+                tma_load_4d_2sm_a(&tmA, fb, sa, cb * 64, w0 + s, h0 + r, n0);
+                tma_load_2d_2sm_a(&tmB, fb, sa + 16384u, kcol, brow);
               } else {
-                mbar_arrive_expect_tx(&full_bar[stage], a_bytes + b_bytes);
-                tma_load_4d(&tmA, &full_bar[stage], sa, cb * 64, w0 + s - p.pad, h0 + r - p.pad, n0);
-                tma_load_2d(&tmB, &full_bar[stage], sa + 16384, kcol, nt * p.block_n);
+                mbar_arrive_expect_tx_a(fb, a_bytes + b_bytes);
+                tma_load_4d_a(&tmA, fb, sa, cb * 64, w0 + s, h0 + r, n0);
+                tma_load_2d_a(&tmB, fb, sa + 16384u, kcol, brow);
               }
-              if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
-      }
+            __syncwarp();
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0 && rank == 0) {
+    // ===================== MMA issuer (leader CTA; warp-uniform loop, one elected lane issues) ===============
+    if (rank == 0) {
       int stage = 0; uint32_t phase = 0; int it = 0;
+      const uint64_t desc_hi = umma_smem_desc_sw128(0, 16, 1024);  // constant fields of both operand descriptors
       for (int u = u0; u < total; u += ustep, ++it) {
         const int buf = it & 1; const uint32_t use = (uint32_t)(it >> 1);
-        mbar_wait(&tempty_bar[buf], (use & 1) ^ 1);
+        mbar_wait_a(tempty0 + 8u * buf, (use & 1) ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem + (uint32_t)(buf * p.block_n);
         for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
+          mbar_wait_a(full0 + 8u * stage, phase);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + (size_t)stage * stage_bytes);
-          const uint32_t b_addr = a_addr + 16384u;
+          if (elect_one_sync()) {
+            const uint32_t a_lo = (smem_base + (uint32_t)stage * stage_bytes) >> 4;
+            const uint64_t da = desc_hi | (uint64_t)a_lo, db = desc_hi | (uint64_t)(a_lo + 1024u);  // B at +16 KB
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t da = umma_smem_desc_sw128(a_addr + k * 32, 16, 1024);
-            const uint64_t db = umma_smem_desc_sw128(b_addr + k * 32, 16, 1024);
-            if constexpr (cta2) umma_bf16_2sm(d_tmem, da, db, p.idesc, (uint32_t)((kb | k) != 0));
-            else umma_bf16(d_tmem, da, db, p.idesc, (uint32_t)((kb | k) != 0));
+            for (int k = 0; k < 4; ++k) {  // +32 B (2 x 16 B units) per UMMA_K = 16
+              if constexpr (cta2) umma_bf16_2sm(d_tmem, da + 2 * k, db + 2 * k, p.idesc, (uint32_t)((kb | k) != 0));
+              else umma_bf16(d_tmem, da + 2 * k, db + 2 * k, p.idesc, (uint32_t)((kb | k) != 0));
+            }
+            if constexpr (cta2) umma_commit_2sm_a(empty0 + 8u * stage, 3); else umma_commit_a(empty0 + 8u * stage);
           }
-          if constexpr (cta2) umma_commit_2sm(&empty_bar[stage], 3); else umma_commit(&empty_bar[stage]);
+          __syncwarp();
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
-        if constexpr (cta2) umma_commit_2sm(&tfull_bar[buf], 3); else umma_commit(&tfull_bar[buf]);
+        if (elect_one_sync()) {
+          if constexpr (cta2) umma_commit_2sm_a(tfull0 + 8u * buf, 3); else umma_commit_a(tfull0 + 8u * buf);
+        }
+        __syncwarp();
       }
     }
   } else {
@@ -434,6 +448,13 @@ int conv_fprop(const Act& x, const void* wk, int R, int S, int pad, const Act& o
   const int out_align = epi.out_fp32 ? 4 : 8;
   if (out.cs % out_align || out.coff % out_align) return DBX_ERR_ARG;
   if (epi.aux_mode && (!epi.aux || epi.aux_cs % 8 || epi.aux_coff % 8)) return DBX_ERR_ARG;
+  if (R == 3 && S == 3 && pad == 1 && x.C == 64 && out.C == 64 && !epi.out_fp32 && block_n <= 0) {
+    const char* e = getenv("DBX_HALO");
+    if (!(e && e[0] == '0')) {  // 64->64 3x3 layers (conv1_2 fwd/dgrad): column-box kernel, resident filter (A/B: DBX_HALO=0)
+      const int rc = conv3x3_halo(x, wk, out, epi, stream);
+      if (rc != DBX_ERR_ARG) return rc;
+    }
+  }
   if (block_n <= 0) block_n = out.C >= 256 ? 256 : out.C;
   if (block_n % 16 || block_n > 256 || block_n < 16) return DBX_ERR_ARG;
 
@@ -557,61 +578,68 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
 
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
+  const uint32_t tfull0 = smem_u32(&tfull_bar[0]), tempty0 = smem_u32(&tempty_bar[0]);
+
   if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      for (int t = blockIdx.x; t < total; t += gridDim.x) {
-        const int split = t / tiles_per_split, rem = t % tiles_per_split;
-        const int m = rem / p.q_tiles, q0 = (rem % p.q_tiles) * p.nb;
-        int nvalid = p.q_total - q0; if (nvalid > p.nb) nvalid = p.nb;
-        const int b_begin = split * p.boxes_per_split;
-        int b_end = b_begin + p.boxes_per_split; if (b_end > p.boxes_total) b_end = p.boxes_total;
-        for (int b = b_begin; b < b_end; ++b) {
-          const int w0 = (b % p.tiles_w) * p.tw;
-          const int h0 = ((b / p.tiles_w) % p.tiles_h) * p.th;
-          const int n0 = (b / (p.tiles_w * p.tiles_h)) * p.tn;
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = smem + (size_t)stage * stage_bytes;
-          mbar_arrive_expect_tx(&full_bar[stage], box_bytes * (2u + (uint32_t)nvalid));
-          tma_load_4d(&tmDy, &full_bar[stage], sa, m * 128, w0, h0, n0);
-          tma_load_4d(&tmDy, &full_bar[stage], sa + box_bytes, m * 128 + 64, w0, h0, n0);
+    // ===================== TMA producer (warp-uniform schedule walk, one elected lane issues) =====================
+    int stage = 0; uint32_t phase = 0;
+    for (int t = blockIdx.x; t < total; t += gridDim.x) {
+      const int split = t / tiles_per_split, rem = t % tiles_per_split;
+      const int m = rem / p.q_tiles, q0 = (rem % p.q_tiles) * p.nb;
+      int nvalid = p.q_total - q0; if (nvalid > p.nb) nvalid = p.nb;
+      const int b_begin = split * p.boxes_per_split;
+      int b_end = b_begin + p.boxes_per_split; if (b_end > p.boxes_total) b_end = p.boxes_total;
+      for (int b = b_begin; b < b_end; ++b) {
+        const int w0 = (b % p.tiles_w) * p.tw;
+        const int h0 = ((b / p.tiles_w) % p.tiles_h) * p.th;
+        const int n0 = (b / (p.tiles_w * p.tiles_h)) * p.tn;
+        mbar_wait_a(empty0 + 8u * stage, phase ^ 1);
+        if (elect_one_sync()) {
+          const uint32_t sa = smem_base + (uint32_t)stage * stage_bytes, fb = full0 + 8u * stage;
+          mbar_arrive_expect_tx_a(fb, box_bytes * (2u + (uint32_t)nvalid));
+          tma_load_4d_a(&tmDy, fb, sa, m * 128, w0, h0, n0);
+          tma_load_4d_a(&tmDy, fb, sa + box_bytes, m * 128 + 64, w0, h0, n0);
           for (int j = 0; j < nvalid; ++j) {
             const int qq = q0 + j, tap = qq / p.cin_blocks, cb = qq % p.cin_blocks;
             const int r = tap / p.S, s = tap % p.S;
-            tma_load_4d(&tmX, &full_bar[stage], sa + box_bytes * (2u + j), cb * 64, w0 + s - p.pad, h0 + r - p.pad, n0);
+            tma_load_4d_a(&tmX, fb, sa + box_bytes * (2u + j), cb * 64, w0 + s - p.pad, h0 + r - p.pad, n0);
           }
-          if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0; int it = 0;
-      const int ksteps = p.kp / 16;
-      for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
-        const int buf = it & 1; const uint32_t use = (uint32_t)(it >> 1);
-        const int split = t / tiles_per_split;
-        const int b_begin = split * p.boxes_per_split;
-        int b_end = b_begin + p.boxes_per_split; if (b_end > p.boxes_total) b_end = p.boxes_total;
-        mbar_wait(&tempty_bar[buf], (use & 1) ^ 1);
+    // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
+    int stage = 0; uint32_t phase = 0; int it = 0;
+    const int ksteps = p.kp / 16;
+    // MN-major SW128: 64-channel atoms LBO apart, groups of 8 pixel rows SBO = 1024 B apart.
+    const uint64_t desc_hi = umma_smem_desc_sw128(0, box_bytes, 1024);
+    for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+      const int buf = it & 1; const uint32_t use = (uint32_t)(it >> 1);
+      const int split = t / tiles_per_split;
+      const int b_begin = split * p.boxes_per_split;
+      int b_end = b_begin + p.boxes_per_split; if (b_end > p.boxes_total) b_end = p.boxes_total;
+      mbar_wait_a(tempty0 + 8u * buf, (use & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem + (uint32_t)(buf * p.block_n);
+      for (int b = b_begin; b < b_end; ++b) {
+        mbar_wait_a(full0 + 8u * stage, phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem + (uint32_t)(buf * p.block_n);
-        for (int b = b_begin; b < b_end; ++b) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + (size_t)stage * stage_bytes);
-          const uint32_t b_addr = a_addr + 2u * box_bytes;
-          for (int ks = 0; ks < ksteps; ++ks) {
-            // MN-major SW128: 64-channel atoms LBO apart, groups of 8 pixel rows SBO = 1024 B apart.
-            const uint64_t da = umma_smem_desc_sw128(a_addr + ks * 2048, box_bytes, 1024);
-            const uint64_t db = umma_smem_desc_sw128(b_addr + ks * 2048, box_bytes, 1024);
+        if (elect_one_sync()) {
+          const uint32_t a_lo = (smem_base + (uint32_t)stage * stage_bytes) >> 4;
+          uint64_t da = desc_hi | (uint64_t)a_lo, db = desc_hi | (uint64_t)(a_lo + ((2u * box_bytes) >> 4));
+          for (int ks = 0; ks < ksteps; ++ks, da += 128, db += 128)  // 16 pixel rows = 2048 B = 128 x 16 B
             umma_bf16(d_tmem, da, db, p.idesc, (uint32_t)((b > b_begin) | (ks != 0)));
-          }
-          umma_commit(&empty_bar[stage]);
-          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          umma_commit_a(empty0 + 8u * stage);
         }
-        umma_commit(&tfull_bar[buf]);
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
+      if (elect_one_sync()) umma_commit_a(tfull0 + 8u * buf);
+      __syncwarp();
     }
   } else {
     const int q = warp & 3;
