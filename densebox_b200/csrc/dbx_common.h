@@ -49,7 +49,10 @@ struct ConvEpilogue {
   int relu = 0;
   const void* aux = nullptr;   // bf16, pixel-aligned with the output
   int aux_cs = 0, aux_coff = 0;
-  int aux_mode = 0;            // 0 none, 1 out = aux>0 ? v : 0 (ReLU backward), 2 out = v*aux (dropout scale)
+  int aux_mode = 0;            // 0 none, 1 out = aux>0 ? v : 0 (ReLU backward), 2 out = v*aux (dropout scale),
+                               // 3 out = v * {0,2} drawn in place from Philox (rng = device {seed, offset})
+  const unsigned long long* rng = nullptr;
+  int rng_channels = 0;        // channel count of the dropped activation (element index = pixel*rng_channels + ch)
   int out_fp32 = 0;            // output element type: 0 bf16, 1 fp32
   int force_cta2 = -1;         // -1 = auto, 0 = never pair CTAs (tcgen05.mma.cta_group::2)
   int epi_bufs = 0;            // 0 = auto; 2/4/8 epilogue staging boxes (short-K GEMMs with a mask want a deep ring)

@@ -436,35 +436,26 @@ int blockdiag_mask(float* g, int rows, int ld, int nh, const int* start, cudaStr
 }
 
 // ------------------------------------------------------------------------------------------------ dropout mask
-// nn.Dropout(p=0.5) in train mode (DenseBox.py:160,176): keep-mask scaled by 2, Philox4x32-10 counter RNG.
-__device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    const uint32_t hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
-    const uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
-    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
-    key.x += 0x9E3779B9u; key.y += 0xBB67AE85u;
-  }
-  return ctr;
-}
-
-__global__ void dropout_mask_kernel(bf16* __restrict__ mask, size_t n8, unsigned long long seed,
+// nn.Dropout(p=0.5) in train mode (DenseBox.py:160,176) as an explicit bf16 {0,2} tensor — the same bits the conv
+// epilogue draws in place (dropout_bits16); used for parity tests and by callers that want to inspect the mask.
+__global__ void dropout_mask_kernel(bf16* __restrict__ mask, size_t n16, unsigned long long seed,
                                     unsigned long long offset) {
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= n8) return;
-  const unsigned long long ctr = idx + offset;
-  const uint4 r = philox4x32(make_uint4((uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, 0u),
-                             make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  if (idx >= n16) return;
+  const uint32_t bits = dropout_bits16((unsigned long long)idx * 16ull, seed, offset);
   const uint32_t two = 0x4000u;  // bf16(2.0)
-  uint32_t w[4] = {r.x, r.y, r.z, r.w}, o[4];
+  uint32_t o[8];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) o[j] = ((w[j] & 0x8000u) ? two : 0u) | ((w[j] & 0x80000000u) ? (two << 16) : 0u);
-  reinterpret_cast<uint4*>(mask)[idx] = make_uint4(o[0], o[1], o[2], o[3]);
+  for (int j = 0; j < 8; ++j)
+    o[j] = (((bits >> (2 * j)) & 1u) ? two : 0u) | (((bits >> (2 * j + 1)) & 1u) ? (two << 16) : 0u);
+  uint4* dst = reinterpret_cast<uint4*>(mask) + idx * 2;
+  dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+  dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
 }
 
 int dropout_mask(void* mask, size_t n, unsigned long long seed, unsigned long long offset, cudaStream_t st) {
-  if (!mask || n % 8) return DBX_ERR_ARG;
-  dropout_mask_kernel<<<grid_for(n / 8, 256), 256, 0, st>>>((bf16*)mask, n / 8, seed, offset);
+  if (!mask || n % 16) return DBX_ERR_ARG;
+  dropout_mask_kernel<<<grid_for(n / 16, 256), 256, 0, st>>>((bf16*)mask, n / 16, seed, offset);
   return (int)cudaGetLastError();
 }
 

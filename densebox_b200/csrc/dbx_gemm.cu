@@ -130,6 +130,7 @@ struct FpropParams {
   int aux_cs, aux_coff, aux_mode;
   void* out;
   int out_cs, out_coff, out_fp32;
+  const unsigned long long* rng; int rng_channels;  // aux_mode 3: in-place Philox dropout
   int cta2;                // 1: CTA pairs drive tcgen05.mma.cta_group::2 (launched with cluster size 2)
   int tma_epi, nbuf, nsb;  // bf16 outputs: epilogue staged through `nbuf` smem buffers, `nsb` 64-column blocks/tile
 };
@@ -160,7 +161,11 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const uint32_t b_bytes = b_rows * 128u;
   const uint32_t stage_bytes = 16384u + b_bytes;
   const int num_kb = p.R * p.S * p.cin_blocks;
-#define DBX_UNIT_TILE(u, nt, mt) const int nt = (u) / m_units, mt = cta2 ? 2 * ((u) % m_units) + (int)rank : (u) % m_units
+  // Unit order: output-channel tile fastest, so the CTAs running at the same time share the SAME pixel tile and the
+  // activations stream from HBM once (the weights of all channel tiles stay L2-resident).  With the pixel tile
+  // fastest the 1x1 head GEMM re-read its 177 MB input once per channel tile (ncu: 709 MB of DRAM reads).
+#define DBX_UNIT_TILE(u, nt, mt) \
+  const int nt = (u) % p.n_tiles, mt = cta2 ? 2 * ((u) / p.n_tiles) + (int)rank : (u) / p.n_tiles
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
@@ -168,7 +173,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], cta2 ? 16 : 8); }
     for (int b = 0; b < 8; ++b) mbar_init(&aux_bar[b], 1);
-    if (p.tma_epi) { tma_prefetch_desc(&tmO); if (p.aux_mode) tma_prefetch_desc(&tmX); }
+    if (p.tma_epi) { tma_prefetch_desc(&tmO); if (p.aux_mode == 1 || p.aux_mode == 2) tma_prefetch_desc(&tmX); }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -274,7 +279,10 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     (mt2 % p.tiles_w) * p.tw, ((mt2 / p.tiles_w) % p.tiles_h) * p.th,
                     (mt2 / (p.tiles_w * p.tiles_h)) * p.tn);
       };
-      if (leader && p.aux_mode)
+      const bool aux_tma = p.aux_mode == 1 || p.aux_mode == 2;
+      unsigned long long rng_seed = 0, rng_off = 0;
+      if (p.aux_mode == 3) { rng_seed = p.rng[0]; rng_off = p.rng[1]; }
+      if (leader && aux_tma)
         for (int q0 = 0; q0 < D && q0 < total_sb; ++q0) issue_aux(q0);
       int it = 0, q = 0;
       for (int u = u0; u < total; u += ustep, ++it) {
@@ -282,6 +290,10 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         DBX_UNIT_TILE(u, nt, mt);
         const int w0 = (mt % p.tiles_w) * p.tw, h0 = ((mt / p.tiles_w) % p.tiles_h) * p.th;
         const int n0 = (mt / (p.tiles_w * p.tiles_h)) * p.tn;
+        // element index of this row's channel 0 in the dropped activation (aux_mode 3)
+        const unsigned long long e_row =
+            (((unsigned long long)(n0 + row / (p.tw * p.th)) * p.out_H + (h0 + (row / p.tw) % p.th)) * p.out_W +
+             (w0 + row % p.tw)) * (unsigned long long)p.rng_channels;
         mbar_wait(&tfull_bar[buf], use & 1);
         tc_fence_after();
         const uint32_t taddr = tmem + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(buf * p.block_n);
@@ -289,13 +301,64 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           if (leader) {
             // the box that is re-filled next (aux prefetch D blocks ahead) must be drained: nbuf - D - 1 stores may pend
             if (nbuf == 8) bulk_wait_read<3>(); else if (nbuf == 4) bulk_wait_read<1>(); else bulk_wait_read<0>();
-            if (p.aux_mode && q + D < total_sb) issue_aux(q + D);
+            if (aux_tma && q + D < total_sb) issue_aux(q + D);
           }
           named_bar_sync(1, 256);
           uint8_t* sb = ring + (size_t)(q % nbuf) * kEpiBuf;
-          if (p.aux_mode) mbar_wait(&aux_bar[q % nbuf], (uint32_t)((q / nbuf) & 1));
+          if (aux_tma) mbar_wait(&aux_bar[q % nbuf], (uint32_t)((q / nbuf) & 1));
           int ncols = p.block_n - j * 64; if (ncols > 64) ncols = 64;
           int cend = half * 32 + 32; if (cend > ncols) cend = ncols;
+          if (cend - half * 32 == 32) {
+            // ---- fast path: this warp's 32 columns in one TMEM load
+            const int c0 = half * 32;
+            uint32_t v[32];
+            tmem_ld_x32(taddr + j * 64 + c0, v);
+            tmem_ld_wait();
+            const int ch = nt * p.block_n + j * 64 + c0;
+            if (row < box_rows) {
+              float f[32];
+#pragma unroll
+              for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+              if (p.bias && ch < p.cout) {
+                const float4* bp = reinterpret_cast<const float4*>(p.bias + ch);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const float4 b4 = __ldg(bp + i);
+                  f[4 * i] += b4.x; f[4 * i + 1] += b4.y; f[4 * i + 2] += b4.z; f[4 * i + 3] += b4.w;
+                }
+              }
+              if (p.relu) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
+              }
+              uint4* sp[4];
+#pragma unroll
+              for (int g = 0; g < 4; ++g)
+                sp[g] = reinterpret_cast<uint4*>(sb + row * 128 + ((((c0 >> 3) + g) ^ (row & 7)) << 4));
+              if (p.aux_mode == 3) {
+                const uint32_t bits = dropout_bits32(e_row + (unsigned long long)ch, rng_seed, rng_off);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) f[i] = ((bits >> i) & 1u) ? f[i] * 2.f : 0.f;
+              } else if (p.aux_mode) {
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                  const uint4 a4 = *sp[g];
+                  const uint32_t au[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {
+                    const float lo = bf16lo(au[i]), hi = bf16hi(au[i]);
+                    float& f0 = f[8 * g + 2 * i]; float& f1 = f[8 * g + 2 * i + 1];
+                    if (p.aux_mode == 1) { f0 = lo > 0.f ? f0 : 0.f; f1 = hi > 0.f ? f1 : 0.f; }
+                    else { f0 *= lo; f1 *= hi; }
+                  }
+                }
+              }
+#pragma unroll
+              for (int g = 0; g < 4; ++g)
+                *sp[g] = make_uint4(pack_bf16x2(f[8 * g], f[8 * g + 1]), pack_bf16x2(f[8 * g + 2], f[8 * g + 3]),
+                                    pack_bf16x2(f[8 * g + 4], f[8 * g + 5]), pack_bf16x2(f[8 * g + 6], f[8 * g + 7]));
+            }
+          } else
           for (int c0 = half * 32; c0 < cend; c0 += 16) {
             uint32_t v[16];
             tmem_ld_x16(taddr + j * 64 + c0, v);
@@ -320,7 +383,11 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               const int cc = c0 >> 3;
               uint4* s0 = reinterpret_cast<uint4*>(sb + row * 128 + (((cc) ^ (row & 7)) << 4));
               uint4* s1 = reinterpret_cast<uint4*>(sb + row * 128 + (((cc + 1) ^ (row & 7)) << 4));
-              if (p.aux_mode) {
+              if (p.aux_mode == 3) {
+                const uint32_t bits = dropout_bits16(e_row + (unsigned long long)ch, rng_seed, rng_off);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) f[i] = ((bits >> i) & 1u) ? f[i] * 2.f : 0.f;
+              } else if (p.aux_mode) {
                 const uint4 a0 = *s0, a1 = *s1;
                 const uint32_t au[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
 #pragma unroll
@@ -447,8 +514,10 @@ int conv_fprop(const Act& x, const void* wk, int R, int S, int pad, const Act& o
   if (out.H != x.H + 2 * pad - R + 1 || out.W != x.W + 2 * pad - S + 1 || out.N != x.N) return DBX_ERR_ARG;
   const int out_align = epi.out_fp32 ? 4 : 8;
   if (out.cs % out_align || out.coff % out_align) return DBX_ERR_ARG;
-  if (epi.aux_mode && (!epi.aux || epi.aux_cs % 8 || epi.aux_coff % 8)) return DBX_ERR_ARG;
-  if (R == 3 && S == 3 && pad == 1 && x.C == 64 && out.C == 64 && !epi.out_fp32 && block_n <= 0) {
+  if ((epi.aux_mode == 1 || epi.aux_mode == 2) && (!epi.aux || epi.aux_cs % 8 || epi.aux_coff % 8)) return DBX_ERR_ARG;
+  if (epi.aux_mode == 3 && (!epi.rng || epi.rng_channels % 128)) return DBX_ERR_ARG;
+  if (R == 3 && S == 3 && pad == 1 && x.C == 64 && out.C == 64 && !epi.out_fp32 && block_n <= 0 &&
+      epi.aux_mode != 3) {
     const char* e = getenv("DBX_HALO");
     if (!(e && e[0] == '0')) {  // 64->64 3x3 layers (conv1_2 fwd/dgrad): column-box kernel, resident filter (A/B: DBX_HALO=0)
       const int rc = conv3x3_halo(x, wk, out, epi, stream);
@@ -459,12 +528,13 @@ int conv_fprop(const Act& x, const void* wk, int R, int S, int pad, const Act& o
   if (block_n % 16 || block_n > 256 || block_n < 16) return DBX_ERR_ARG;
 
   Tile t = choose_tile(out.W, out.H, out.N, false);
-  const int tma_epi = epi.out_fp32 ? 0 : 1;
+  int tma_epi = epi.out_fp32 ? 0 : 1;
+  { const char* e = getenv("DBX_DIRECT_EPI"); if (e && e[0] == '1' && epi.aux_mode != 3) tma_epi = 0; }  // A/B switch
   // CTA pairs (tcgen05.mma.cta_group::2) whenever the B tile is worth halving
-  // (measured round 1: no gain over single CTAs on this path — the big layers are bound by wave quantisation and
-  // MMA issue, not by operand traffic — so pairing is opt-in: ConvEpilogue::force_cta2 = 1 or DBX_CTA2=1)
-  const bool cta2_ok = tma_epi && block_n >= 128 && block_n % 32 == 0 && t.count() >= 2 && num_sms() >= 2;
-  int cta2 = (cta2_ok && epi.force_cta2 == 1) ? 1 : 0;
+  // (measured round 1: +4..6 % on the N = 256 layers once the MMA issue loop was lean; before that the kernel was
+  // issue-bound and pairing changed nothing.  ConvEpilogue::force_cta2 = 0 or DBX_CTA2=0 switches it off.)
+  const bool cta2_ok = tma_epi && block_n >= 256 && t.count() >= 2 && num_sms() >= 2;
+  int cta2 = (cta2_ok && epi.force_cta2 != 0) ? 1 : 0;
   { const char* e = getenv("DBX_CTA2"); if (e && cta2_ok) cta2 = e[0] == '1'; }  // A/B switch for measurements
   CUtensorMap tmA, tmB, tmO, tmX;
   int rc = encode_act_map(&tmA, x, t);
@@ -474,7 +544,7 @@ int conv_fprop(const Act& x, const void* wk, int R, int S, int pad, const Act& o
   if (tma_epi) {
     rc = encode_act_map(&tmO, out, t);
     if (rc) return rc;
-    if (epi.aux_mode) {
+    if (epi.aux_mode == 1 || epi.aux_mode == 2) {
       Act ax = out;
       ax.ptr = const_cast<void*>(epi.aux); ax.cs = epi.aux_cs; ax.coff = epi.aux_coff;
       rc = encode_act_map(&tmX, ax, t);
@@ -483,7 +553,7 @@ int conv_fprop(const Act& x, const void* wk, int R, int S, int pad, const Act& o
       tmX = tmO;
     }
   } else {
-    if (epi.aux_mode) return DBX_ERR_ARG;  // fp32 outputs (tiny head GEMMs) take no mask
+    if (epi.aux_mode && epi.out_fp32) return DBX_ERR_ARG;  // fp32 outputs (tiny head GEMMs) take no mask
     tmO = tmA; tmX = tmA;
   }
 
@@ -510,6 +580,7 @@ int conv_fprop(const Act& x, const void* wk, int R, int S, int pad, const Act& o
   p.bias = epi.bias; p.relu = epi.relu;
   p.aux = (const bf16*)epi.aux; p.aux_cs = epi.aux_cs; p.aux_coff = epi.aux_coff; p.aux_mode = epi.aux_mode;
   p.out = out.ptr; p.out_cs = out.cs; p.out_coff = out.coff; p.out_fp32 = epi.out_fp32;
+  p.rng = epi.rng; p.rng_channels = epi.rng_channels;
 
   static int attr_rc1 = set_max_smem((const void*)conv_fprop_kernel<false>);
   static int attr_rc2 = set_max_smem((const void*)conv_fprop_kernel<true>);
@@ -550,6 +621,7 @@ struct WgradParams {
   uint32_t idesc, tmem_cols;
 };
 
+template <bool kCta2>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ CUtensorMap tmX,
                   const WgradParams p) {
@@ -560,21 +632,33 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // cta2: a CTA pair works on two 128-row output-channel tiles with one tcgen05.mma.cta_group::2 per K step; each CTA
+  // stages its own dY boxes and HALF of the shifted-input boxes (the wgrad mainloop is bound by TMA delivery).
+  constexpr bool cta2 = kCta2;
+  uint32_t rank = 0u;
+  if constexpr (cta2) rank = cluster_ctarank();
+  const int u0 = cta2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int ustep = cta2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int m_units = cta2 ? (p.m_tiles + 1) >> 1 : p.m_tiles;
+  const int nbl = cta2 ? p.nb >> 1 : p.nb;                    // input boxes staged by THIS CTA
   const uint32_t box_bytes = (uint32_t)p.kp * 128u;           // one [kp pixels][64 ch] tile
-  const uint32_t stage_bytes = box_bytes * (2u + (uint32_t)p.nb);
-  const int tiles_per_split = p.m_tiles * p.q_tiles;
+  const uint32_t stage_bytes = box_bytes * (2u + (uint32_t)nbl);
+  const int tiles_per_split = m_units * p.q_tiles;
   const int total = tiles_per_split * p.splits;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmDy);
     tma_prefetch_desc(&tmX);
     for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 4); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], cta2 ? 8 : 4); }
     fence_barrier_init();
   }
-  if (warp == 1) { tmem_alloc(&tmem_base_s, p.tmem_cols); tmem_relinquish(); }
+  if (warp == 1) {
+    if constexpr (cta2) { tmem_alloc_2sm(&tmem_base_s, p.tmem_cols); tmem_relinquish_2sm(); }
+    else { tmem_alloc(&tmem_base_s, p.tmem_cols); tmem_relinquish(); }
+  }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (cta2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
 
@@ -585,10 +669,12 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
   if (warp == 0) {
     // ===================== TMA producer (warp-uniform schedule walk, one elected lane issues) =====================
     int stage = 0; uint32_t phase = 0;
-    for (int t = blockIdx.x; t < total; t += gridDim.x) {
+    for (int t = u0; t < total; t += ustep) {
       const int split = t / tiles_per_split, rem = t % tiles_per_split;
-      const int m = rem / p.q_tiles, q0 = (rem % p.q_tiles) * p.nb;
+      const int m = (cta2 ? 2 : 1) * (rem / p.q_tiles) + (int)rank, q0 = (rem % p.q_tiles) * p.nb;
       int nvalid = p.q_total - q0; if (nvalid > p.nb) nvalid = p.nb;
+      const int j0 = (int)rank * nbl;                           // first input box of this CTA
+      int jn = nvalid - j0; if (jn > nbl) jn = nbl; if (jn < 0) jn = 0;
       const int b_begin = split * p.boxes_per_split;
       int b_end = b_begin + p.boxes_per_split; if (b_end > p.boxes_total) b_end = p.boxes_total;
       for (int b = b_begin; b < b_end; ++b) {
@@ -598,13 +684,22 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
         mbar_wait_a(empty0 + 8u * stage, phase ^ 1);
         if (elect_one_sync()) {
           const uint32_t sa = smem_base + (uint32_t)stage * stage_bytes, fb = full0 + 8u * stage;
-          mbar_arrive_expect_tx_a(fb, box_bytes * (2u + (uint32_t)nvalid));
-          tma_load_4d_a(&tmDy, fb, sa, m * 128, w0, h0, n0);
-          tma_load_4d_a(&tmDy, fb, sa + box_bytes, m * 128 + 64, w0, h0, n0);
-          for (int j = 0; j < nvalid; ++j) {
-            const int qq = q0 + j, tap = qq / p.cin_blocks, cb = qq % p.cin_blocks;
+          if constexpr (cta2) {
+            if (rank == 0) mbar_arrive_expect_tx_a(fb, box_bytes * (4u + (uint32_t)nvalid));  // both CTAs' bytes
+            tma_load_4d_2sm_a(&tmDy, fb, sa, m * 128, w0, h0, n0);
+            tma_load_4d_2sm_a(&tmDy, fb, sa + box_bytes, m * 128 + 64, w0, h0, n0);
+          } else {
+            mbar_arrive_expect_tx_a(fb, box_bytes * (2u + (uint32_t)nvalid));
+            tma_load_4d_a(&tmDy, fb, sa, m * 128, w0, h0, n0);
+            tma_load_4d_a(&tmDy, fb, sa + box_bytes, m * 128 + 64, w0, h0, n0);
+          }
+          for (int j = 0; j < jn; ++j) {
+            const int qq = q0 + j0 + j, tap = qq / p.cin_blocks, cb = qq % p.cin_blocks;
             const int r = tap / p.S, s = tap % p.S;
-            tma_load_4d_a(&tmX, fb, sa + box_bytes * (2u + j), cb * 64, w0 + s - p.pad, h0 + r - p.pad, n0);
+            if constexpr (cta2)
+              tma_load_4d_2sm_a(&tmX, fb, sa + box_bytes * (2u + j), cb * 64, w0 + s - p.pad, h0 + r - p.pad, n0);
+            else
+              tma_load_4d_a(&tmX, fb, sa + box_bytes * (2u + j), cb * 64, w0 + s - p.pad, h0 + r - p.pad, n0);
           }
         }
         __syncwarp();
@@ -617,7 +712,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
     const int ksteps = p.kp / 16;
     // MN-major SW128: 64-channel atoms LBO apart, groups of 8 pixel rows SBO = 1024 B apart.
     const uint64_t desc_hi = umma_smem_desc_sw128(0, box_bytes, 1024);
-    for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+    if (rank == 0)
+    for (int t = u0; t < total; t += ustep, ++it) {
       const int buf = it & 1; const uint32_t use = (uint32_t)(it >> 1);
       const int split = t / tiles_per_split;
       const int b_begin = split * p.boxes_per_split;
@@ -631,23 +727,27 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
         if (elect_one_sync()) {
           const uint32_t a_lo = (smem_base + (uint32_t)stage * stage_bytes) >> 4;
           uint64_t da = desc_hi | (uint64_t)a_lo, db = desc_hi | (uint64_t)(a_lo + ((2u * box_bytes) >> 4));
-          for (int ks = 0; ks < ksteps; ++ks, da += 128, db += 128)  // 16 pixel rows = 2048 B = 128 x 16 B
-            umma_bf16(d_tmem, da, db, p.idesc, (uint32_t)((b > b_begin) | (ks != 0)));
-          umma_commit_a(empty0 + 8u * stage);
+          for (int ks = 0; ks < ksteps; ++ks, da += 128, db += 128) {  // 16 pixel rows = 2048 B = 128 x 16 B
+            if constexpr (cta2) umma_bf16_2sm(d_tmem, da, db, p.idesc, (uint32_t)((b > b_begin) | (ks != 0)));
+            else umma_bf16(d_tmem, da, db, p.idesc, (uint32_t)((b > b_begin) | (ks != 0)));
+          }
+          if constexpr (cta2) umma_commit_2sm_a(empty0 + 8u * stage, 3); else umma_commit_a(empty0 + 8u * stage);
         }
         __syncwarp();
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
-      if (elect_one_sync()) umma_commit_a(tfull0 + 8u * buf);
+      if (elect_one_sync()) {
+        if constexpr (cta2) umma_commit_2sm_a(tfull0 + 8u * buf, 3); else umma_commit_a(tfull0 + 8u * buf);
+      }
       __syncwarp();
     }
   } else {
     const int q = warp & 3;
     int it = 0;
-    for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+    for (int t = u0; t < total; t += ustep, ++it) {
       const int buf = it & 1; const uint32_t use = (uint32_t)(it >> 1);
       const int rem = t % tiles_per_split;
-      const int m = rem / p.q_tiles, q0 = (rem % p.q_tiles) * p.nb;
+      const int m = (cta2 ? 2 : 1) * (rem / p.q_tiles) + (int)rank, q0 = (rem % p.q_tiles) * p.nb;
       const int row = m * 128 + q * 32 + lane;
       const bool valid = row < p.cout;
       mbar_wait(&tfull_bar[buf], use & 1);
@@ -667,12 +767,16 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+      if (lane == 0) { if constexpr (cta2) mbar_arrive_cluster(&tempty_bar[buf], 0); else mbar_arrive(&tempty_bar[buf]); }
     }
   }
   tc_fence_before();
-  __syncthreads();
-  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem, p.tmem_cols); }
+  __syncwarp();
+  if constexpr (cta2) cluster_sync_all(); else __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    if constexpr (cta2) tmem_dealloc_2sm(tmem, p.tmem_cols); else tmem_dealloc(tmem, p.tmem_cols);
+  }
 }
 
 int conv_wgrad(const Act& x, const Act& dy, int R, int S, int pad, float* dw, int block_n, cudaStream_t stream) {
@@ -702,27 +806,41 @@ int conv_wgrad(const Act& x, const Act& dy, int R, int S, int pad, float* dw, in
   p.cin_blocks = x.C / 64; p.q_total = q_total; p.nb = block_n / 64; p.block_n = block_n;
   p.m_tiles = (dy.C + 127) / 128; p.q_tiles = (q_total + p.nb - 1) / p.nb;
   p.boxes_total = t.count();
-  const int tiles = p.m_tiles * p.q_tiles;
-  int splits = num_sms() / tiles;
+  // CTA pairs (cta_group::2) share the shifted-input boxes: worth it from two output-channel tiles up
+  int cta2 = (p.m_tiles >= 2 && block_n == 256 && num_sms() >= 2) ? 1 : 0;
+  { const char* e = getenv("DBX_CTA2"); if (e && e[0] == '0') cta2 = 0; }
+  const int m_units = cta2 ? (p.m_tiles + 1) / 2 : p.m_tiles;
+  const int tiles = m_units * p.q_tiles;
+  const int workers = cta2 ? num_sms() / 2 : num_sms();
+  int splits = workers / tiles;
   if (splits < 1) splits = 1;
   if (splits > p.boxes_total) splits = p.boxes_total;
   p.boxes_per_split = (p.boxes_total + splits - 1) / splits;
   p.splits = (p.boxes_total + p.boxes_per_split - 1) / p.boxes_per_split;
   p.cout = dy.C; p.ldw = R * S * x.C; p.dw = dw;
-  const int stage_bytes = p.kp * 128 * (2 + p.nb);
+  const int stage_bytes = p.kp * 128 * (2 + (cta2 ? p.nb / 2 : p.nb));
   p.stages = kSmemBudget / stage_bytes;
   if (p.stages > kMaxStages) p.stages = kMaxStages;
   if (p.stages < 2) return DBX_ERR_ARG;
-  p.idesc = umma_idesc_bf16(128, block_n, 1, 1);
+  p.idesc = umma_idesc_bf16(cta2 ? 256 : 128, block_n, 1, 1);
   p.tmem_cols = tmem_cols_for(2 * block_n);
 
-  static int attr_rc = set_max_smem((const void*)conv_wgrad_kernel);
-  if (attr_rc) return attr_rc;
+  static int attr_rc1 = set_max_smem((const void*)conv_wgrad_kernel<false>);
+  static int attr_rc2 = set_max_smem((const void*)conv_wgrad_kernel<true>);
+  if (attr_rc1 || attr_rc2) return attr_rc1 ? attr_rc1 : attr_rc2;
   const int total = tiles * p.splits;
-  const int grid = total < num_sms() ? total : num_sms();
   const size_t smem = (size_t)p.stages * stage_bytes + 1024;
-  conv_wgrad_kernel<<<grid, kThreads, smem, stream>>>(tmDy, tmX, p);
-  return (int)cudaGetLastError();
+  cudaLaunchConfig_t cfg{};
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cta2 ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cfg.gridDim = dim3((cta2 ? 2 : 1) * (total < workers ? total : workers));
+  if (cta2) return (int)cudaLaunchKernelEx(&cfg, conv_wgrad_kernel<true>, tmDy, tmX, p);
+  return (int)cudaLaunchKernelEx(&cfg, conv_wgrad_kernel<false>, tmDy, tmX, p);
 }
 
 }  // namespace dbx

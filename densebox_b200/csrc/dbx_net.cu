@@ -174,6 +174,7 @@ struct Net {
     add_buf("w32", flat_n * 4);
     add_buf("wk", flat_n * 2);
     add_buf("wd", wd_n * 2);
+    add_buf("rng", 256);      // {seed, offset} (2 x u64) of the in-epilogue dropout draw
     add_buf("scalars", 256);  // [0] loss f32, [1] counter u32, [2..3] info i32, [16..] loss_partial
     add_buf("loss_partial", (size_t)N * 4);
     add_buf("col0", px1 * 64 * 2);
@@ -296,9 +297,13 @@ struct Net {
   }
 
 
-  // dropout_mode: 0 = eval (identity), 1 = draw a Philox mask (seed, offset), 2 = use the mask already in `drop`
+  // dropout_mode: 0 = eval (identity); 1 = Philox draw inside the conv epilogues from (seed, offset); 2 = multiply
+  // by the {0,2} bf16 mask the caller wrote into `drop`; 3 = like 1 but (seed, offset) are read from the `rng`
+  // region as the caller left it (CUDA-graph replays: update the region between replays).
+  unsigned long long rng_host[2] = {0, 0};
   int forward(const float* x, int dropout_mode, unsigned long long seed, unsigned long long offset, cudaStream_t st) {
     if (!x) return DBX_ERR_ARG;
+    if (dropout_mode < 0 || dropout_mode > 3) return DBX_ERR_ARG;
     if (dropout_mode && !train) return DBX_ERR_STATE;
     const int h2 = H / 2, w2 = W / 2, h4 = H / 4, w4 = W / 4, h8 = H / 8, w8 = W / 8;
     Act col0 = act("col0", H, W, 64), a11 = act("a11", H, W, 64), a12 = act("a12", H, W, 64);
@@ -325,12 +330,17 @@ struct Net {
     DBX_TRY(conv(a42, "conv4_3", 3, 1, a43, true, nullptr, 0, 0, false, 0, st));
     DBX_TRY(conv(a43, "conv4_4", 3, 1, a44, true, nullptr, 0, 0, false, 0, st));
     DBX_K("upsample_fwd", 0.0, upsample_bilinear_fwd(a44, fus_up, st));
-    const void* drop = nullptr;
-    if (dropout_mode) {
-      drop = buf("drop");
-      if (dropout_mode == 1) DBX_K("dropout_mask", 0.0, dropout_mask(buf("drop"), (size_t)N * h4 * w4 * 512 * nh, seed, offset, st));
+    if (dropout_mode == 1) {
+      rng_host[0] = seed; rng_host[1] = offset;
+      DBX_TRY((int)cudaMemcpyAsync(buf("rng"), rng_host, 16, cudaMemcpyHostToDevice, st));
     }
-    DBX_TRY(conv(fus, "heads1", 1, 0, hd, false, drop, 512 * nh, drop ? 2 : 0, false, 0, st));
+    {
+      ConvEpilogue e;
+      e.bias = bias_of("heads1");
+      if (dropout_mode == 2) { e.aux = buf("drop"); e.aux_cs = 512 * nh; e.aux_mode = 2; e.epi_bufs = 4; }
+      else if (dropout_mode) { e.aux_mode = 3; e.rng = (const unsigned long long*)buf("rng"); e.rng_channels = 512 * nh; }
+      DBX_K("fprop:heads1", 2.0 * pixels(hd) * macs_of("heads1"), conv_fprop(fus, wk_of("heads1"), 1, 1, 0, hd, e, 0, st));
+    }
     DBX_TRY(conv(hd, "heads2", 1, 0, ho, false, nullptr, 0, 0, true, 0, st));
     if (variant >= 1) {
       Act rp = act("rp", h8, w8, 64), r1 = act("r1", h8 - 2, w8 - 2, 64), r2 = act("r2", h8 - 6, w8 - 6, 64);
@@ -341,11 +351,11 @@ struct Net {
       DBX_K("upsample_fwd", 0.0, upsample_bilinear_fwd(r2, rup, st));
       DBX_TRY(conv(rup, "conv6_3_det", 1, 0, rf, false, nullptr, 0, 0, true, 0, st));
     }
-    dropout_used = dropout_mode != 0;
+    drop_mode = dropout_mode == 2 ? 2 : (dropout_mode ? 3 : 0);
     forward_done = true;
     return DBX_OK;
   }
-  bool dropout_used = false;
+  int drop_mode = 0;  // how the last forward dropped: 0 none, 2 mask buffer, 3 Philox in place
 
   // ---- loss (+ gradients w.r.t. the head outputs)
   int loss(const float* bbox, const float* vertices, const float* labels, const long long* rand_idx, int rand_stride,
@@ -414,8 +424,8 @@ struct Net {
       const Group& g = groups[group_id("heads2")];
       DBX_K("blockdiag_mask", 0.0, blockdiag_mask(G32() + g.w_off, g.rows, g.ld, nh, ch_start, st));
       ConvEpilogue e;
-      if (dropout_used) { e.aux = buf("drop"); e.aux_cs = 512 * nh; e.aux_mode = 2; }
-      e.epi_bufs = 8;  // K = 64: the kernel is its epilogue, prefetch the mask 4 blocks ahead
+      if (drop_mode == 2) { e.aux = buf("drop"); e.aux_cs = 512 * nh; e.aux_mode = 2; e.epi_bufs = 8; }
+      else if (drop_mode == 3) { e.aux_mode = 3; e.rng = (const unsigned long long*)buf("rng"); e.rng_channels = 512 * nh; }
       DBX_K("dgrad:heads2", 2.0 * pixels(d_head64) * macs_of("heads2"),
             conv_fprop(d_head64, wd_of("heads2"), 1, 1, 0, d_hd, e, 0, st));
     }

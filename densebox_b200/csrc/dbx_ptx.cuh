@@ -277,6 +277,17 @@ __device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t* v) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,"
+      "%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---------------------------------------------------------------- UMMA descriptors
@@ -302,6 +313,40 @@ __host__ __device__ __forceinline__ uint32_t umma_idesc_bf16(int M, int N, int a
   d |= (uint32_t)(N >> 3) << 17;
   d |= (uint32_t)(M >> 4) << 24;
   return d;
+}
+
+// ---------------------------------------------------------------- dropout RNG
+// Philox4x32-10.  nn.Dropout(p=0.5) (DenseBox.py:160,176): element e of the [pixels][C] activation is kept iff bit
+// (e & 127) of philox(counter = (e >> 7) + offset, key = seed) is set; kept values are scaled by 2.
+__device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += 0x9E3779B9u; key.y += 0xBB67AE85u;
+  }
+  return ctr;
+}
+// keep-bits of the 16 consecutive elements starting at element index e (e % 16 == 0)
+__device__ __forceinline__ uint32_t dropout_bits16(unsigned long long e, unsigned long long seed,
+                                                   unsigned long long offset) {
+  const unsigned long long c = (e >> 7) + offset;
+  const uint4 r = philox4x32(make_uint4((uint32_t)c, (uint32_t)(c >> 32), 0u, 0u),
+                             make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  const uint32_t b = (uint32_t)(e & 127ull);
+  const uint32_t w = (b >> 5) == 0 ? r.x : ((b >> 5) == 1 ? r.y : ((b >> 5) == 2 ? r.z : r.w));
+  return (w >> (b & 31u)) & 0xFFFFu;
+}
+
+// keep-bits of the 32 consecutive elements starting at element index e (e % 32 == 0)
+__device__ __forceinline__ uint32_t dropout_bits32(unsigned long long e, unsigned long long seed,
+                                                   unsigned long long offset) {
+  const unsigned long long c = (e >> 7) + offset;
+  const uint4 r = philox4x32(make_uint4((uint32_t)c, (uint32_t)(c >> 32), 0u, 0u),
+                             make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  const uint32_t b = (uint32_t)(e & 127ull) >> 5;
+  return b == 0 ? r.x : (b == 1 ? r.y : (b == 2 ? r.z : r.w));
 }
 
 // ---------------------------------------------------------------- misc

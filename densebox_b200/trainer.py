@@ -44,6 +44,9 @@ class DenseBoxTrainer:
         self.use_graph = use_cuda_graph
         self._graph_fb = self._graph_sgd = None
         self._graph_lr = None
+        self._rng = self.eng.buffer("rng", torch.int64)
+        drop_elems = self.eng.buffer("drop", torch.bfloat16).numel()
+        self._rng_stride = (drop_elems + 127) // 128  # Philox calls consumed by one step
         self.load_from_module()
 
     # ---- parameters
@@ -71,7 +74,7 @@ class DenseBoxTrainer:
 
     def _fwd_loss_bwd(self):
         e = self.eng
-        e.forward(self.x, dropout_mode=2 if self.dropout else 0)
+        e.forward(self.x, dropout_mode=3 if self.dropout else 0)  # Philox in the epilogues, state in the rng region
         ll, ld, lm = self.lambdas
         e.loss(self.bbox, vertices=self.vertices if self.variant != "densebox" else None,
                labels=self.labels if self.use_labels else None, rand_idx=self.rand,
@@ -100,11 +103,9 @@ class DenseBoxTrainer:
                 self.lm_rand.copy_(torch.randint(0, 3600, (self.B, 4), device=self.device))
             else:
                 self._stage(self.lm_rand, lm_rand_neg_idx)
-        if self.dropout:
-            drop = e.buffer("drop", torch.bfloat16)
-            check(lib().dbx_dropout_mask(ptr(drop), ctypes.c_ulonglong(drop.numel()), ctypes.c_ulonglong(self.seed),
-                                         ctypes.c_ulonglong(self.step_no * (drop.numel() // 8)), stream_ptr()),
-                  "dropout_mask")
+        if self.dropout:  # a fresh mask per step: advance the Philox counter offset (device side, graph safe)
+            self._rng[0] = self.seed
+            self._rng[1] = self.step_no * self._rng_stride
         if self.world > 1:
             check(lib().dbx_count_positives(ptr(self.bbox), ptr(self.labels if self.use_labels else None),
                                             c_int(self.B), ptr(self.gpos), stream_ptr()), "count_positives")

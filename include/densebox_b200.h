@@ -72,7 +72,8 @@ int dbx_loss_fwd_bwd(const float* head, int HC, const float* rf, int RC, const f
                      unsigned char* mask_out, unsigned char* lm_mask_out, void* stream);
 /* Positive pixels of a label shard (sum of the clipped init_score_map boxes, DenseBox.py:2864) -> *out (device). */
 int dbx_count_positives(const float* bbox, const float* labels, int B, int* out, void* stream);
-/* nn.Dropout(p=0.5) keep-mask x2 as bf16, Philox4x32-10 keyed by (seed, offset); n % 8 == 0. */
+/* nn.Dropout(p=0.5) keep-mask x2 as an explicit bf16 tensor — the same Philox4x32-10 bits the conv epilogues draw
+ * in place for dropout_mode 1/3 (element e: bit e&127 of philox(counter (e>>7)+offset, key seed)); n % 16 == 0. */
 int dbx_dropout_mask(void* mask, unsigned long long n, unsigned long long seed, unsigned long long offset,
                      void* stream);
 
@@ -105,8 +106,10 @@ int dbx_net_get_grad(void* handle, const char* name, int is_bias, float* dst, lo
 int dbx_net_refresh_dgrad(void* handle, void* stream);
 
 /* net.forward(X) — DenseBox.py:180-228 / :412-473 / :674-738. x: fp32 NCHW [N,3,H,W] device pointer.
- * dropout_mode 0 = eval(), 1 = train() with a Philox mask drawn from (seed, offset), 2 = train() with the {0,2}
- * bf16 mask the caller has written into the "drop" region (parity tests inject the oracle's mask). */
+ * dropout_mode 0 = eval(); 1 = train(), nn.Dropout drawn inside the conv epilogues from Philox(seed, offset);
+ * 2 = train() with the {0,2} bf16 mask the caller has written into the "drop" region (parity tests inject the
+ * oracle's mask); 3 = like 1 but {seed, offset} are read from the "rng" region (2 x u64) as the caller left it
+ * (CUDA-graph replays). */
 int dbx_net_forward(void* handle, const float* x, int dropout_mode, unsigned long long seed,
                     unsigned long long offset, void* stream);
 

@@ -205,3 +205,39 @@ if __name__ == "__main__":
         except Exception as e:
             import traceback; traceback.print_exc()
             print(fn.__name__, "FAIL", repr(e)[:600], flush=True)
+
+
+def test_inplace_philox_dropout_equals_explicit_mask():
+    """dropout_mode 1 (mask drawn inside the conv epilogues) == dropout_mode 2 fed the mask that dbx_dropout_mask
+    materialises from the same (seed, offset): identical head outputs and identical gradients, bit for bit."""
+    import ctypes
+    from densebox_b200 import NetEngine
+    from densebox_b200._lib import check, lib, ptr, stream_ptr
+    vgg, net = build("densebox")
+    net = net.cuda()
+    B = 2
+    x, lab, rand, _ = make_inputs(B, "densebox")
+    res = []
+    for mode in (1, 2):
+        eng = NetEngine("densebox", B, 240, 240, train=True)
+        for name in ["conv1_1", "conv1_2", "conv2_1", "conv2_2", "conv3_1", "conv3_2", "conv3_4", "conv4_1", "conv4_2",
+                     "conv4_3", "conv4_4", "conv5_1_det", "conv5_1_loc", "conv5_2_det", "conv5_2_loc"]:
+            w, b = net._wb(name)
+            eng.set_param(name, w, b)
+        eng.refresh_dgrad()
+        if mode == 2:
+            drop = eng.buffer("drop", torch.bfloat16)
+            check(lib().dbx_dropout_mask(ptr(drop), ctypes.c_ulonglong(drop.numel()), ctypes.c_ulonglong(77),
+                                         ctypes.c_ulonglong(5), stream_ptr()), "dropout_mask")
+            frac = drop.float().mean().item() / 2
+            assert 0.49 < frac < 0.51
+        eng.forward(x.cuda(), dropout_mode=mode, seed=77, offset=5)
+        eng.loss(torch.tensor(lab["bbox"]).cuda(), rand_idx=torch.tensor(rand).cuda())
+        eng.zero_grad()
+        eng.backward()
+        torch.cuda.synchronize()
+        res.append((eng.head_out().clone(), eng.flat_grads().clone(), float(eng.loss_value())))
+    assert torch.equal(res[0][0], res[1][0])
+    assert res[0][2] == res[1][2]
+    # wgrad accumulates with fp32 atomics (order varies run to run): compare to accumulation noise
+    assert (res[0][1] - res[1][1]).abs().max().item() <= 1e-4 * res[1][1].abs().max().item()

@@ -34,8 +34,8 @@ def test_decode_nms_batch_vs_oracle(hw):
     g = torch.Generator().manual_seed(h)
     score = torch.randn(N, 1, h, w, generator=g)
     # clustered boxes so that NMS actually suppresses: loc offsets make neighbouring cells decode to similar boxes
-    loc = torch.stack([torch.full((N, h, w), -2.0), torch.full((N, h, w), -2.0), torch.full((N, h, w), 3.0),
-                       torch.full((N, h, w), 3.0)], 1) + 0.3 * torch.randn(N, 4, h, w, generator=g)
+    loc = torch.stack([torch.full((N, h, w), 2.0), torch.full((N, h, w), 2.0), torch.full((N, h, w), -3.0),
+                       torch.full((N, h, w), -3.0)], 1) + 0.3 * torch.randn(N, 4, h, w, generator=g)
     bump = torch.zeros(N, 1, h, w)
     bump[:, :, h // 2 - 1:h // 2 + 2, w // 2 - 1:w // 2 + 2] = 6.0  # a 3x3 cluster of top scores
     score = score + bump

@@ -44,10 +44,10 @@ def main():
         dw = torch.zeros(cout, R * R * cin, device="cuda")
         flops = 2.0 * B * H * H * cin * cout * R * R
         for bn in ([0] if cout <= 128 else [256]):
-            for c2 in (("0", "1") if cin <= 128 and R == 3 else ("1",)):
-                os.environ["DBX_HALO"] = c2
+            for c2 in ("0", "1"):
+                os.environ["DBX_CTA2"] = c2
                 tf = timeit(lambda: ops.conv_fprop(x, wk, R, R, pad, out, bias=bias, relu=True, block_n=bn))
-                print("%-16s fprop bn=%3d halo=%s %8.3f ms %8.1f TFLOP/s" % (name, bn, c2, tf, flops / tf * 1e-9),
+                print("%-16s fprop bn=%3d cta2=%s %8.3f ms %8.1f TFLOP/s" % (name, bn, c2, tf, flops / tf * 1e-9),
                       flush=True)
         tw = timeit(lambda: ops.conv_wgrad(x, dy, R, R, pad, dw))
         print("%-16s wgrad        %8.3f ms %8.1f TFLOP/s" % (name, tw, flops / tw * 1e-9), flush=True)
