@@ -278,7 +278,7 @@ def main():
         conv = [fam.get("fprop", [0, 0, 0]), fam.get("dgrad", [0, 0, 0])]
         fl = conv[0][0] + conv[1][0]; tm = conv[0][1] + conv[1][1]
         ach = fl / tm * 1e-9
-        roof = {"kernel": "conv_fprop_kernel (tcgen05 implicit GEMM: %d fprop + %d dgrad launches per step)"
+        roof = {"kernel": "conv_fprop_kernel + conv3x3_halo_kernel (tcgen05 implicit GEMM: %d fprop + %d dgrad launches per step)"
                           % (conv[0][2], conv[1][2]),
                 "bound": "tensor", "achieved": round(ach, 1), "peak": pk["tf_sustained"], "unit": "TFLOP/s",
                 "frac": round(ach / pk["tf_sustained"], 4), "traffic": None, "peak_source": pk["source"],
