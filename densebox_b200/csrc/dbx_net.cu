@@ -263,7 +263,10 @@ struct Net {
                           s_r, s_s, st);
   }
   // bf16 dgrad-layout copies of every filter (call after the weights changed, before backward)
+  bool dgrad_stale = false;   // set by sgd(): the flipped filters are rebuilt on the side stream during forward
+  bool dgrad_pending = false; // transposes in flight on the side stream
   int refresh_dgrad(cudaStream_t st) {
+    dgrad_stale = false;
     for (auto& g : groups) {
       if (!g.need_dgrad) continue;
       DBX_K("transpose_dgrad", 0.0, transpose_dgrad(WK() + g.w_off, WD() + g.wd_off, g.rows, g.T, g.cin_pad, g.kpad, st));
@@ -289,11 +292,33 @@ struct Net {
           conv_fprop(dy, wd_of(grp), R, R, R - 1 - pad, dx, e, 0, st));
     return DBX_OK;
   }
+  // Weight and bias gradients run on a side stream.  The critical chain of the backward pass is dgrad -> pool /
+  // upsample backward -> dgrad ...; wgrad(l) only needs dZ(l).  With wgrads queued on a second stream the HBM-bound
+  // element-wise kernels of the chain (and the colsum bias gradients, 8 KB smem) co-reside with a persistent tensor
+  // kernel instead of leaving the tensor cores idle.
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool side_used = false;
   int wgrad(const Act& x, const Act& dy, const char* grp, int R, int pad, cudaStream_t st) {
+    if (side && !profiling) {
+      DBX_TRY((int)cudaEventRecord(ev_fork, st));
+      DBX_TRY((int)cudaStreamWaitEvent(side, ev_fork, 0));
+      launches += 2;
+      DBX_TRY(colsum(dy, gb_of(grp), side));
+      DBX_TRY(conv_wgrad(x, dy, R, R, pad, gw_of(grp), 0, side));
+      side_used = true;
+      return DBX_OK;
+    }
+    DBX_K((std::string("colsum:") + grp).c_str(), 0.0, colsum(dy, gb_of(grp), st));
     DBX_K((std::string("wgrad:") + grp).c_str(), 2.0 * pixels(dy) * macs_of(grp),
           conv_wgrad(x, dy, R, R, pad, gw_of(grp), 0, st));
-    DBX_K((std::string("colsum:") + grp).c_str(), 0.0, colsum(dy, gb_of(grp), st));
     return DBX_OK;
+  }
+  int join_side(cudaStream_t st) {
+    if (!side_used) return DBX_OK;
+    side_used = false;
+    DBX_TRY((int)cudaEventRecord(ev_join, side));
+    return (int)cudaStreamWaitEvent(st, ev_join, 0);
   }
 
 
@@ -314,6 +339,13 @@ struct Net {
     Act p3 = act("p3", h8, w8, 256), a41 = act("a41", h8, w8, 512), a42 = act("a42", h8, w8, 512);
     Act a43 = act("a43", h8, w8, 512), a44 = act("a44", h8, w8, 512);
     Act hd = act("hd", h4, w4, 512 * nh), ho = act("head_out", h4, w4, HC);
+    if (dgrad_stale && side && !profiling) {  // overlap the filter re-layout with the forward pass
+      DBX_TRY((int)cudaEventRecord(ev_fork, st));
+      DBX_TRY((int)cudaStreamWaitEvent(side, ev_fork, 0));
+      DBX_TRY(refresh_dgrad(side));
+      DBX_TRY((int)cudaEventRecord(ev_join, side));
+      dgrad_pending = true;
+    }
     DBX_K("im2col", 0.0, im2col3x3_c3(x, col0.ptr, N, H, W, 0, st));
     DBX_TRY(conv(col0, "conv1_1", 1, 0, a11, true, nullptr, 0, 0, false, 0, st));
     DBX_TRY(conv(a11, "conv1_2", 3, 1, a12, true, nullptr, 0, 0, false, 0, st));
@@ -386,6 +418,8 @@ struct Net {
   // ---- backward: d_head / d_rf (bf16, written by loss() or by the caller) -> parameter gradients in g32 (+=)
   int backward(cudaStream_t st) {
     if (!train || !forward_done) return DBX_ERR_STATE;
+    if (dgrad_pending) { DBX_TRY((int)cudaStreamWaitEvent(st, ev_join, 0)); dgrad_pending = false; }
+    if (dgrad_stale) DBX_TRY(refresh_dgrad(st));
     const int h2 = H / 2, w2 = W / 2, h4 = H / 4, w4 = W / 4, h8 = H / 8, w8 = W / 8;
     Act col0 = act("col0", H, W, 64), a11 = act("a11", H, W, 64), a12 = act("a12", H, W, 64);
     Act p1 = act("p1", h2, w2, 64), a21 = act("a21", h2, w2, 128), a22 = act("a22", h2, w2, 128);
@@ -422,7 +456,8 @@ struct Net {
     DBX_TRY(wgrad(hd, d_headC, "heads2", 1, 0, st));
     {
       const Group& g = groups[group_id("heads2")];
-      DBX_K("blockdiag_mask", 0.0, blockdiag_mask(G32() + g.w_off, g.rows, g.ld, nh, ch_start, st));
+      if (side && !profiling) { ++launches; DBX_TRY(blockdiag_mask(G32() + g.w_off, g.rows, g.ld, nh, ch_start, side)); }
+      else DBX_K("blockdiag_mask", 0.0, blockdiag_mask(G32() + g.w_off, g.rows, g.ld, nh, ch_start, st));
       ConvEpilogue e;
       if (drop_mode == 2) { e.aux = buf("drop"); e.aux_cs = 512 * nh; e.aux_mode = 2; e.epi_bufs = 8; }
       else if (drop_mode == 3) { e.aux_mode = 3; e.rng = (const unsigned long long*)buf("rng"); e.rng_channels = 512 * nh; }
@@ -460,7 +495,7 @@ struct Net {
     DBX_TRY(wgrad(a11, d_a12, "conv1_2", 3, 1, st));
     DBX_TRY(dgrad(d_a12, "conv1_2", 3, 1, d_a11, &a11, st));
     DBX_TRY(wgrad(col0, d_a11, "conv1_1", 1, 0, st));
-    return DBX_OK;
+    return join_side(st);
   }
 
   int zero_grad(cudaStream_t st) {
@@ -472,7 +507,8 @@ struct Net {
     if (!train) return DBX_ERR_STATE;
     DBX_K("sgd", 0.0, sgd_step(W32(), G32(), V32(), WK(), flat_n, lr, momentum, wd, sgd_steps == 0 ? 1 : 0, 1, st));
     ++sgd_steps;
-    return refresh_dgrad(st);
+    dgrad_stale = true;
+    return DBX_OK;
   }
 };
 
@@ -504,12 +540,27 @@ int dbx_net_create(int variant, int N, int H, int W, int train, void* workspace,
   n->build(variant, N, H, W, train);
   n->ws = (char*)workspace;
   rc = n->init((cudaStream_t)stream);
+  if (!rc && train) {
+    rc = (int)cudaStreamCreateWithFlags(&n->side, cudaStreamNonBlocking);
+    if (!rc) rc = (int)cudaEventCreateWithFlags(&n->ev_fork, cudaEventDisableTiming);
+    if (!rc) rc = (int)cudaEventCreateWithFlags(&n->ev_join, cudaEventDisableTiming);
+  }
   if (rc) { delete n; return rc; }
   *handle = n;
   return DBX_OK;
 }
 
-int dbx_net_destroy(void* handle) { delete (Net*)handle; return DBX_OK; }
+int dbx_net_destroy(void* handle) {
+  Net* n = (Net*)handle;
+  if (n) {
+    if (n->ev_fork) cudaEventDestroy(n->ev_fork);
+    if (n->ev_join) cudaEventDestroy(n->ev_join);
+    if (n->side) cudaStreamDestroy(n->side);
+    n->prof_clear();
+    delete n;
+  }
+  return DBX_OK;
+}
 
 int dbx_net_buffer(void* handle, const char* name, void** ptr, size_t* bytes) {
   if (!handle || !name || !ptr) return DBX_ERR_ARG;
