@@ -619,6 +619,7 @@ struct WgradParams {
   float* dw;
   int stages;
   uint32_t idesc, tmem_cols;
+  int colbox;  // Cin = 64, 3x3: one column-shifted 8x18 input box per stage serves the three filter rows (N = 192)
 };
 
 template <bool kCta2>
@@ -642,7 +643,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
   const int m_units = cta2 ? (p.m_tiles + 1) >> 1 : p.m_tiles;
   const int nbl = cta2 ? p.nb >> 1 : p.nb;                    // input boxes staged by THIS CTA
   const uint32_t box_bytes = (uint32_t)p.kp * 128u;           // one [kp pixels][64 ch] tile
-  const uint32_t stage_bytes = box_bytes * (2u + (uint32_t)nbl);
+  const uint32_t stage_bytes = p.colbox ? 2u * box_bytes + 18432u : box_bytes * (2u + (uint32_t)nbl);
   const int tiles_per_split = m_units * p.q_tiles;
   const int total = tiles_per_split * p.splits;
 
@@ -688,12 +689,19 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
             if (rank == 0) mbar_arrive_expect_tx_a(fb, box_bytes * (4u + (uint32_t)nvalid));  // both CTAs' bytes
             tma_load_4d_2sm_a(&tmDy, fb, sa, m * 128, w0, h0, n0);
             tma_load_4d_2sm_a(&tmDy, fb, sa + box_bytes, m * 128 + 64, w0, h0, n0);
+          } else if (p.colbox) {
+            // q0 = filter column s: dY tile(s) + ONE input box shifted by s-1 columns, one row of halo above/below
+            const bool two = m * 128 + 64 < p.cout;
+            mbar_arrive_expect_tx_a(fb, (two ? 2u : 1u) * box_bytes + 18432u);
+            tma_load_4d_a(&tmDy, fb, sa, m * 128, w0, h0, n0);
+            if (two) tma_load_4d_a(&tmDy, fb, sa + box_bytes, m * 128 + 64, w0, h0, n0);
+            tma_load_4d_a(&tmX, fb, sa + 2u * box_bytes, 0, w0 + q0 - 1, h0 - 1, n0);
           } else {
             mbar_arrive_expect_tx_a(fb, box_bytes * (2u + (uint32_t)nvalid));
             tma_load_4d_a(&tmDy, fb, sa, m * 128, w0, h0, n0);
             tma_load_4d_a(&tmDy, fb, sa + box_bytes, m * 128 + 64, w0, h0, n0);
           }
-          for (int j = 0; j < jn; ++j) {
+          for (int j = 0; j < (p.colbox ? 0 : jn); ++j) {
             const int qq = q0 + j0 + j, tap = qq / p.cin_blocks, cb = qq % p.cin_blocks;
             const int r = tap / p.S, s = tap % p.S;
             if constexpr (cta2)
@@ -726,7 +734,10 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
         tc_fence_after();
         if (elect_one_sync()) {
           const uint32_t a_lo = (smem_base + (uint32_t)stage * stage_bytes) >> 4;
-          uint64_t da = desc_hi | (uint64_t)a_lo, db = desc_hi | (uint64_t)(a_lo + ((2u * box_bytes) >> 4));
+          uint64_t da = desc_hi | (uint64_t)a_lo;
+          // colbox: the three filter rows are the same box shifted by 8 pixel rows = one 1024-B atom (LBO = 1024)
+          uint64_t db = (p.colbox ? umma_smem_desc_sw128(0, 1024, 1024) : desc_hi) |
+                        (uint64_t)(a_lo + ((2u * box_bytes) >> 4));
           for (int ks = 0; ks < ksteps; ++ks, da += 128, db += 128) {  // 16 pixel rows = 2048 B = 128 x 16 B
             if constexpr (cta2) umma_bf16_2sm(d_tmem, da, db, p.idesc, (uint32_t)((b > b_begin) | (ks != 0)));
             else umma_bf16(d_tmem, da, db, p.idesc, (uint32_t)((b > b_begin) | (ks != 0)));
@@ -753,15 +764,17 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
       mbar_wait(&tfull_bar[buf], use & 1);
       tc_fence_after();
       const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * p.block_n);
-      float* drow = p.dw + (size_t)row * p.ldw + (size_t)q0 * 64;
+      float* drow = p.dw + (size_t)row * p.ldw + (p.colbox ? (size_t)0 : (size_t)q0 * 64);
       for (int c0 = 0; c0 < p.block_n; c0 += 16) {
         uint32_t v[16];
         tmem_ld_x16(taddr + c0, v);
         tmem_ld_wait();
-        if (valid && (q0 + c0 / 64) < p.q_total) {
+        // colbox: column block c0/64 is filter row r, q0 is filter column s -> tap r*3+s of dw[co][tap][ci]
+        float* dst = p.colbox ? drow + ((c0 >> 6) * 3 + q0) * 64 + (c0 & 63) : drow + c0;
+        if (valid && (p.colbox || (q0 + c0 / 64) < p.q_total)) {
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            red_add_v4(drow + c0 + 4 * j, __uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+            red_add_v4(dst + 4 * j, __uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
                        __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
         }
       }
@@ -780,6 +793,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
 }
 
 int conv_wgrad(const Act& x, const Act& dy, int R, int S, int pad, float* dw, int block_n, cudaStream_t stream) {
+  const int block_n_in = block_n;
   if (!x.ptr || !dy.ptr || !dw) return DBX_ERR_ARG;
   if (x.C % 64 || dy.C % 16) return DBX_ERR_ARG;
   if (dy.H != x.H + 2 * pad - R + 1 || dy.W != x.W + 2 * pad - S + 1 || dy.N != x.N) return DBX_ERR_ARG;
@@ -793,11 +807,26 @@ int conv_wgrad(const Act& x, const Act& dy, int R, int S, int pad, float* dw, in
   if (block_n % 64 || block_n > 256 || block_n < 64) return DBX_ERR_ARG;
 
   Tile t = choose_tile(dy.W, dy.H, dy.N, true);
+  // Cin = 64 3x3 layers (conv1_2, conv2_1): column-box variant, see WgradParams::colbox
+  int colbox = (R == 3 && S == 3 && pad == 1 && x.C == 64 && block_n_in <= 0) ? 1 : 0;
+  { const char* e = getenv("DBX_COLBOX"); if (e && e[0] == '0') colbox = 0; }
   CUtensorMap tmDy, tmX;
-  int rc = encode_act_map(&tmDy, dy, t);
-  if (rc) return rc;
-  rc = encode_act_map(&tmX, x, t);
-  if (rc) return rc;
+  int rc;
+  if (colbox) {
+    t.tw = 8; t.th = 16; t.tn = 1;
+    t.tiles_w = (dy.W + 7) / 8; t.tiles_h = (dy.H + 15) / 16; t.tiles_n = dy.N;
+    block_n = 192;
+    Tile tx = t; tx.th = 18;
+    rc = encode_act_map(&tmDy, dy, t);
+    if (rc) return rc;
+    rc = encode_act_map(&tmX, x, tx);
+    if (rc) return rc;
+  } else {
+    rc = encode_act_map(&tmDy, dy, t);
+    if (rc) return rc;
+    rc = encode_act_map(&tmX, x, t);
+    if (rc) return rc;
+  }
 
   WgradParams p{};
   p.tw = t.tw; p.th = t.th; p.tn = t.tn; p.tiles_w = t.tiles_w; p.tiles_h = t.tiles_h; p.tiles_n = t.tiles_n;
@@ -805,9 +834,11 @@ int conv_wgrad(const Act& x, const Act& dy, int R, int S, int pad, float* dw, in
   p.kp = t.rows();
   p.cin_blocks = x.C / 64; p.q_total = q_total; p.nb = block_n / 64; p.block_n = block_n;
   p.m_tiles = (dy.C + 127) / 128; p.q_tiles = (q_total + p.nb - 1) / p.nb;
+  p.colbox = colbox;
+  if (colbox) { p.q_tiles = 3; p.nb = 1; }  // q-tile = filter column s
   p.boxes_total = t.count();
   // CTA pairs (cta_group::2) share the shifted-input boxes: worth it from two output-channel tiles up
-  int cta2 = (p.m_tiles >= 2 && block_n == 256 && num_sms() >= 2) ? 1 : 0;
+  int cta2 = (!colbox && p.m_tiles >= 2 && block_n == 256 && num_sms() >= 2) ? 1 : 0;
   { const char* e = getenv("DBX_CTA2"); if (e && e[0] == '0') cta2 = 0; }
   const int m_units = cta2 ? (p.m_tiles + 1) / 2 : p.m_tiles;
   const int tiles = m_units * p.q_tiles;
@@ -818,7 +849,7 @@ int conv_wgrad(const Act& x, const Act& dy, int R, int S, int pad, float* dw, in
   p.boxes_per_split = (p.boxes_total + splits - 1) / splits;
   p.splits = (p.boxes_total + p.boxes_per_split - 1) / p.boxes_per_split;
   p.cout = dy.C; p.ldw = R * S * x.C; p.dw = dw;
-  const int stage_bytes = p.kp * 128 * (2 + (cta2 ? p.nb / 2 : p.nb));
+  const int stage_bytes = colbox ? 2 * p.kp * 128 + 18432 : p.kp * 128 * (2 + (cta2 ? p.nb / 2 : p.nb));
   p.stages = kSmemBudget / stage_bytes;
   if (p.stages > kMaxStages) p.stages = kMaxStages;
   if (p.stages < 2) return DBX_ERR_ARG;
