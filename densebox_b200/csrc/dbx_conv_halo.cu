@@ -11,6 +11,7 @@
 // conv_fprop_kernel (bias / ReLU / mask in a swizzled smem box, TMA store).
 #include "dbx_common.h"
 #include "dbx_ptx.cuh"
+#include "dbx_epilogue.cuh"
 
 namespace dbx {
 
@@ -18,7 +19,6 @@ static constexpr int kHaloThreads = 320;        // 1 producer + 1 MMA + 8 epilog
 static constexpr int kSBox = 18 * 8 * 128;      // one column-shifted box: 18 rows x 8 pixels x 64 channels = 18 KB
 static constexpr int kMaxASlots = 8;
 static constexpr int kMaxBSlots = 12;
-static constexpr int kEpiBox = 16384;
 static constexpr int kHaloSmem = 230400;
 
 struct HaloParams {
@@ -27,7 +27,7 @@ struct HaloParams {
   int cout;
   int resident;            // whole filter resident in smem (n_tiles == 1)
   int a_slots, b_slots;    // ring depths (column boxes, per-tap filter tiles)
-  int nbuf, nsb;           // epilogue staging
+  int nbuf, nbuf_log2, nsb;  // epilogue staging boxes (2/4/8), 64-column blocks per tile
   uint32_t idesc, tmem_cols;
   const float* bias;
   int relu, aux_mode;
@@ -44,7 +44,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
   const uint32_t b_tile = (uint32_t)p.block_n * 128u;               // one (tap, 64-channel slice) filter tile
   const int kb_per_tile = 9 * p.cin_blocks;
   const int nb = p.resident ? kb_per_tile : p.b_slots;
@@ -111,25 +111,24 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     const uint64_t desc_hi = umma_smem_desc_sw128(0, 16, 1024);
-    if (p.resident && p.cin_blocks == 1 && p.a_slots == 6) {
+    if (p.resident && p.cin_blocks == 1) {
       // Fully unrolled issue path for the resident-filter case (conv1_2 and its data gradient): with N = 64 one MMA
-      // lasts 32 cycles, so every instruction between two UTCHMMAs counts.  A tile uses slots {0,1,2} or {3,4,5}.
+      // lasts 32 cycles, so every instruction between two UTCHMMAs counts.
       mbar_wait_a(bfull0, 0);
       tc_fence_after();
       const uint32_t a_lo0 = a_base >> 4, b_lo0 = b_base >> 4, bt = b_tile >> 4;
-      int it = 0;
+      int it = 0; uint32_t as = 0, aph = 0;
       for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
         const int buf = it & 1; const uint32_t use = (uint32_t)(it >> 1);
-        const uint32_t slot0 = (uint32_t)(it & 1) * 3u;
         mbar_wait_a(tempty0 + 8u * buf, (use & 1) ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem + (uint32_t)(buf * p.block_n);
 #pragma unroll
         for (int s = 0; s < 3; ++s) {
-          mbar_wait_a(afull0 + 8u * (slot0 + s), use & 1);
+          mbar_wait_a(afull0 + 8u * as, aph);
           tc_fence_after();
           if (elect_one_sync()) {
-            const uint64_t da0 = desc_hi | (uint64_t)(a_lo0 + (slot0 + s) * (uint32_t)(kSBox >> 4));
+            const uint64_t da0 = desc_hi | (uint64_t)(a_lo0 + as * (uint32_t)(kSBox >> 4));
             const uint64_t db0 = desc_hi | (uint64_t)(b_lo0 + (uint32_t)(s * 3) * bt);
 #pragma unroll
             for (int r = 0; r < 3; ++r)
@@ -137,10 +136,11 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               for (int k = 0; k < 4; ++k)
                 umma_bf16(d_tmem, da0 + 64 * r + 2 * k, db0 + (uint64_t)r * bt + 2 * k, p.idesc,
                           (uint32_t)((s | r | k) != 0));
-            umma_commit_a(aempty0 + 8u * (slot0 + s));
+            umma_commit_a(aempty0 + 8u * as);
             if (s == 2) umma_commit_a(tfull0 + 8u * buf);
           }
           __syncwarp();
+          if (++as == (uint32_t)p.a_slots) { as = 0; aph ^= 1; }
         }
       }
     } else {
@@ -184,97 +184,20 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     }
   } else {
-    // ===================== epilogue: TMEM -> (bias, ReLU, mask) -> smem box -> TMA store =====================
-    const int q4 = warp & 3, half = (warp - 2) >> 2;
-    const int row = q4 * 32 + lane;
-    const bool leader = threadIdx.x == 64;
-    const int nsb = p.nsb, nbuf = p.nbuf, D = p.nbuf >> 1;
+    // ===================== epilogue: the shared TMA-staged epilogue (dbx_epilogue.cuh) =====================
+    EpiArgs ea;
+    ea.bias = p.bias; ea.cout = p.cout; ea.relu = p.relu; ea.aux_mode = p.aux_mode;
+    ea.block_n = p.block_n; ea.nsb = p.nsb; ea.nbuf_log2 = p.nbuf_log2;
+    ea.tw = 8; ea.th = 16; ea.box_rows = 128;
+    ea.out_W = 0; ea.out_H = 0; ea.rng = nullptr; ea.rng_channels = 0;
     const int my_tiles = (int)blockIdx.x < total ? (total - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-    const int total_sb = my_tiles * nsb;
-    auto issue_aux = [&](int qq) {
-      const int t2 = blockIdx.x + (qq / nsb) * gridDim.x, j2 = qq % nsb;
-      const int nt2 = t2 / p.m_tiles, mt2 = t2 % p.m_tiles;
-      const int b2 = qq % nbuf;
-      mbar_arrive_expect_tx(&aux_bar[b2], (uint32_t)kEpiBox);
-      tma_load_4d(&tmX, &aux_bar[b2], ring + (size_t)b2 * kEpiBox, nt2 * p.block_n + j2 * 64, (mt2 % p.tiles_w) * 8,
-                  ((mt2 / p.tiles_w) % p.tiles_h) * 16, mt2 / (p.tiles_w * p.tiles_h));
+    auto tile_of = [&](int it, int& nt, int& w0, int& h0, int& n0) {
+      const int t = (int)blockIdx.x + it * (int)gridDim.x;
+      const int mt = t % p.m_tiles;
+      nt = t / p.m_tiles;
+      w0 = (mt % p.tiles_w) * 8; h0 = ((mt / p.tiles_w) % p.tiles_h) * 16; n0 = mt / (p.tiles_w * p.tiles_h);
     };
-    if (leader && p.aux_mode)
-      for (int q0 = 0; q0 < D && q0 < total_sb; ++q0) issue_aux(q0);
-    int it = 0, q = 0;
-    for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
-      const int buf = it & 1; const uint32_t use = (uint32_t)(it >> 1);
-      const int nt = t / p.m_tiles, mt = t % p.m_tiles;
-      const int w0 = (mt % p.tiles_w) * 8, h0 = ((mt / p.tiles_w) % p.tiles_h) * 16;
-      const int n0 = mt / (p.tiles_w * p.tiles_h);
-      mbar_wait_a(tfull0 + 8u * buf, use & 1);
-      tc_fence_after();
-      const uint32_t taddr = tmem + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(buf * p.block_n);
-      for (int j = 0; j < nsb; ++j, ++q) {
-        if (leader) {
-          if (nbuf == 8) bulk_wait_read<3>(); else if (nbuf == 4) bulk_wait_read<1>(); else bulk_wait_read<0>();
-          if (p.aux_mode && q + D < total_sb) issue_aux(q + D);
-        }
-        named_bar_sync(1, 256);
-        uint8_t* sb = ring + (size_t)(q % nbuf) * kEpiBox;
-        if (p.aux_mode) mbar_wait(&aux_bar[q % nbuf], (uint32_t)((q / nbuf) & 1));
-        int ncols = p.block_n - j * 64; if (ncols > 64) ncols = 64;
-        int cend = half * 32 + 32; if (cend > ncols) cend = ncols;
-        for (int c0 = half * 32; c0 < cend; c0 += 16) {
-          uint32_t v[16];
-          tmem_ld_x16(taddr + j * 64 + c0, v);
-          tmem_ld_wait();
-          const int ch = nt * p.block_n + j * 64 + c0;
-          float f[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
-          if (p.bias && ch < p.cout) {
-            const float4* bp = reinterpret_cast<const float4*>(p.bias + ch);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float4 b4 = __ldg(bp + i);
-              f[4 * i] += b4.x; f[4 * i + 1] += b4.y; f[4 * i + 2] += b4.z; f[4 * i + 3] += b4.w;
-            }
-          }
-          if (p.relu) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
-          }
-          const int cc = c0 >> 3;
-          uint4* s0 = reinterpret_cast<uint4*>(sb + row * 128 + (((cc) ^ (row & 7)) << 4));
-          uint4* s1 = reinterpret_cast<uint4*>(sb + row * 128 + (((cc + 1) ^ (row & 7)) << 4));
-          if (p.aux_mode) {
-            const uint4 a0 = *s0, a1 = *s1;
-            const uint32_t au[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float lo = bf16lo(au[i]), hi = bf16hi(au[i]);
-              if (p.aux_mode == 1) {
-                f[2 * i] = lo > 0.f ? f[2 * i] : 0.f;
-                f[2 * i + 1] = hi > 0.f ? f[2 * i + 1] : 0.f;
-              } else {
-                f[2 * i] *= lo;
-                f[2 * i + 1] *= hi;
-              }
-            }
-          }
-          *s0 = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
-                           pack_bf16x2(f[6], f[7]));
-          *s1 = make_uint4(pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]), pack_bf16x2(f[12], f[13]),
-                           pack_bf16x2(f[14], f[15]));
-        }
-        fence_proxy_async_smem();
-        named_bar_sync(2, 256);
-        if (leader) {
-          tma_store_4d(&tmO, sb, nt * p.block_n + j * 64, w0, h0, n0);
-          bulk_commit();
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[buf]);
-    }
-    if (leader) bulk_wait_all();
+    epilogue_tma<false>(ea, &tmO, &tmX, ring, aux_bar, tfull_bar, tempty_bar, tmem, my_tiles, tile_of);
   }
   tc_fence_before();
   __syncthreads();
@@ -301,20 +224,26 @@ int conv3x3_halo(const Act& x, const void* wk, const Act& out, const ConvEpilogu
   const int b_tile = p.block_n * 128;
   const int kb_per_tile = 9 * p.cin_blocks;
   p.nsb = (p.block_n + 63) / 64;
-  p.nbuf = 2;
+  // smem plan: resident filter (whole filter, n_tiles == 1) when it leaves room for >= 4 column boxes and 2 staging
+  // boxes; the short-K resident layers are epilogue-bound (ncu: 19 B/clk of operand traffic), so they trade column
+  // boxes for a 4-deep staging ring (the mask prefetch needs it: D = nbuf / 2 sub-blocks of lead).
   p.resident = (p.n_tiles == 1 && kb_per_tile * b_tile <= 80 * 1024) ? 1 : 0;
-  p.a_slots = 6;
-  int avail = kHaloSmem - p.a_slots * kSBox - p.nbuf * kEpiBox;
+  p.nbuf = 2;
   if (p.resident) {
     p.b_slots = 0;
-    avail -= kb_per_tile * b_tile;
-    if (avail < 0) return DBX_ERR_ARG;
-    if (avail >= 2 * kEpiBox) { p.nbuf = 4; avail -= 2 * kEpiBox; }
+    int avail = kHaloSmem - kb_per_tile * b_tile;
+    p.nbuf = 4; p.a_slots = (avail - p.nbuf * kEpiBox) / kSBox;
+    if (p.a_slots < 4) { p.nbuf = 2; p.a_slots = (avail - p.nbuf * kEpiBox) / kSBox; }
+    if (p.a_slots > kMaxASlots) p.a_slots = kMaxASlots;
+    if (p.a_slots < 3) return DBX_ERR_ARG;
   } else {
+    p.a_slots = 6;
+    int avail = kHaloSmem - p.a_slots * kSBox - p.nbuf * kEpiBox;
     p.b_slots = avail / b_tile;
     if (p.b_slots > kMaxBSlots) p.b_slots = kMaxBSlots;
     if (p.b_slots < 3) return DBX_ERR_ARG;
   }
+  p.nbuf_log2 = p.nbuf == 8 ? 3 : (p.nbuf == 4 ? 2 : 1);
   const size_t smem = (size_t)p.a_slots * kSBox + (size_t)(p.resident ? kb_per_tile : p.b_slots) * b_tile +
                       (size_t)p.nbuf * kEpiBox + 1024;
   if (smem > (size_t)kHaloSmem + 1024) return DBX_ERR_ARG;

@@ -14,6 +14,7 @@
 //   warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue.
 #include "dbx_common.h"
 #include "dbx_ptx.cuh"
+#include "dbx_epilogue.cuh"
 #include <mutex>
 #include <stdlib.h>
 
@@ -132,7 +133,7 @@ struct FpropParams {
   int out_cs, out_coff, out_fp32;
   const unsigned long long* rng; int rng_channels;  // aux_mode 3: in-place Philox dropout
   int cta2;                // 1: CTA pairs drive tcgen05.mma.cta_group::2 (launched with cluster size 2)
-  int tma_epi, nbuf, nsb;  // bf16 outputs: epilogue staged through `nbuf` smem buffers, `nsb` 64-column blocks/tile
+  int tma_epi, nbuf, nbuf_log2, nsb;  // bf16 outputs: epilogue staged through `nbuf` (2/4/8) smem boxes, `nsb` 64-column blocks/tile
 };
 
 template <bool kCta2>
@@ -258,168 +259,21 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   } else {
     // ===================== epilogue (warps 2..5 -> TMEM lane quarters 2,3,0,1) =====================
     if (p.tma_epi) {
-      // bf16 outputs: TMEM -> registers -> (bias, ReLU, mask) -> swizzled smem box -> TMA store.  The mask tile is
-      // TMA-loaded into the same box two 64-column blocks ahead and transformed in place, so no epilogue thread
-      // ever waits on a global load and every global access of the kernel is a bulk tensor copy.
-      const int q4 = warp & 3, half = (warp - 2) >> 2;  // TMEM lane quarter, 32-column half of each 64-column block
-      const int row = q4 * 32 + lane;
-      const bool leader = threadIdx.x == 64;
-      const int box_rows = p.tw * p.th * p.tn;
-      const uint32_t box_bytes = (uint32_t)box_rows * 128u;
-      uint8_t* ring = smem + (size_t)p.stages * stage_bytes;
-      const int nsb = p.nsb, nbuf = p.nbuf, D = p.nbuf >> 1;
+      // bf16 outputs: the shared TMA-staged epilogue (dbx_epilogue.cuh)
+      EpiArgs ea;
+      ea.bias = p.bias; ea.cout = p.cout; ea.relu = p.relu; ea.aux_mode = p.aux_mode;
+      ea.block_n = p.block_n; ea.nsb = p.nsb; ea.nbuf_log2 = p.nbuf_log2;
+      ea.tw = p.tw; ea.th = p.th; ea.box_rows = p.tw * p.th * p.tn;
+      ea.out_W = p.out_W; ea.out_H = p.out_H; ea.rng = p.rng; ea.rng_channels = p.rng_channels;
       const int my_tiles = u0 < total ? (total - 1 - u0) / ustep + 1 : 0;
-      const int total_sb = my_tiles * nsb;
-      auto issue_aux = [&](int qq) {
-        const int u2 = u0 + (qq / nsb) * ustep, j2 = qq % nsb;
-        DBX_UNIT_TILE(u2, nt2, mt2);
-        const int b2 = qq % nbuf;
-        mbar_arrive_expect_tx(&aux_bar[b2], box_bytes);
-        tma_load_4d(&tmX, &aux_bar[b2], ring + (size_t)b2 * kEpiBuf, nt2 * p.block_n + j2 * 64,
-                    (mt2 % p.tiles_w) * p.tw, ((mt2 / p.tiles_w) % p.tiles_h) * p.th,
-                    (mt2 / (p.tiles_w * p.tiles_h)) * p.tn);
+      auto tile_of = [&](int it, int& nt, int& w0, int& h0, int& n0) {
+        DBX_UNIT_TILE(u0 + it * ustep, nt_, mt_);
+        nt = nt_;
+        w0 = (mt_ % p.tiles_w) * p.tw; h0 = ((mt_ / p.tiles_w) % p.tiles_h) * p.th;
+        n0 = (mt_ / (p.tiles_w * p.tiles_h)) * p.tn;
       };
-      const bool aux_tma = p.aux_mode == 1 || p.aux_mode == 2;
-      unsigned long long rng_seed = 0, rng_off = 0;
-      if (p.aux_mode == 3) { rng_seed = p.rng[0]; rng_off = p.rng[1]; }
-      if (leader && aux_tma)
-        for (int q0 = 0; q0 < D && q0 < total_sb; ++q0) issue_aux(q0);
-      int it = 0, q = 0;
-      for (int u = u0; u < total; u += ustep, ++it) {
-        const int buf = it & 1; const uint32_t use = (uint32_t)(it >> 1);
-        DBX_UNIT_TILE(u, nt, mt);
-        const int w0 = (mt % p.tiles_w) * p.tw, h0 = ((mt / p.tiles_w) % p.tiles_h) * p.th;
-        const int n0 = (mt / (p.tiles_w * p.tiles_h)) * p.tn;
-        // element index of this row's channel 0 in the dropped activation (aux_mode 3)
-        const unsigned long long e_row =
-            (((unsigned long long)(n0 + row / (p.tw * p.th)) * p.out_H + (h0 + (row / p.tw) % p.th)) * p.out_W +
-             (w0 + row % p.tw)) * (unsigned long long)p.rng_channels;
-        mbar_wait(&tfull_bar[buf], use & 1);
-        tc_fence_after();
-        const uint32_t taddr = tmem + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(buf * p.block_n);
-        for (int j = 0; j < nsb; ++j, ++q) {
-          if (leader) {
-            // the box that is re-filled next (aux prefetch D blocks ahead) must be drained: nbuf - D - 1 stores may pend
-            if (nbuf == 8) bulk_wait_read<3>(); else if (nbuf == 4) bulk_wait_read<1>(); else bulk_wait_read<0>();
-            if (aux_tma && q + D < total_sb) issue_aux(q + D);
-          }
-          named_bar_sync(1, 256);
-          uint8_t* sb = ring + (size_t)(q % nbuf) * kEpiBuf;
-          if (aux_tma) mbar_wait(&aux_bar[q % nbuf], (uint32_t)((q / nbuf) & 1));
-          int ncols = p.block_n - j * 64; if (ncols > 64) ncols = 64;
-          int cend = half * 32 + 32; if (cend > ncols) cend = ncols;
-          if (cend - half * 32 == 32) {
-            // ---- fast path: this warp's 32 columns in one TMEM load
-            const int c0 = half * 32;
-            uint32_t v[32];
-            tmem_ld_x32(taddr + j * 64 + c0, v);
-            tmem_ld_wait();
-            const int ch = nt * p.block_n + j * 64 + c0;
-            if (row < box_rows) {
-              float f[32];
-#pragma unroll
-              for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
-              if (p.bias && ch < p.cout) {
-                const float4* bp = reinterpret_cast<const float4*>(p.bias + ch);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  const float4 b4 = __ldg(bp + i);
-                  f[4 * i] += b4.x; f[4 * i + 1] += b4.y; f[4 * i + 2] += b4.z; f[4 * i + 3] += b4.w;
-                }
-              }
-              if (p.relu) {
-#pragma unroll
-                for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
-              }
-              uint4* sp[4];
-#pragma unroll
-              for (int g = 0; g < 4; ++g)
-                sp[g] = reinterpret_cast<uint4*>(sb + row * 128 + ((((c0 >> 3) + g) ^ (row & 7)) << 4));
-              if (p.aux_mode == 3) {
-                const uint32_t bits = dropout_bits32(e_row + (unsigned long long)ch, rng_seed, rng_off);
-#pragma unroll
-                for (int i = 0; i < 32; ++i) f[i] = ((bits >> i) & 1u) ? f[i] * 2.f : 0.f;
-              } else if (p.aux_mode) {
-#pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                  const uint4 a4 = *sp[g];
-                  const uint32_t au[4] = {a4.x, a4.y, a4.z, a4.w};
-#pragma unroll
-                  for (int i = 0; i < 4; ++i) {
-                    const float lo = bf16lo(au[i]), hi = bf16hi(au[i]);
-                    float& f0 = f[8 * g + 2 * i]; float& f1 = f[8 * g + 2 * i + 1];
-                    if (p.aux_mode == 1) { f0 = lo > 0.f ? f0 : 0.f; f1 = hi > 0.f ? f1 : 0.f; }
-                    else { f0 *= lo; f1 *= hi; }
-                  }
-                }
-              }
-#pragma unroll
-              for (int g = 0; g < 4; ++g)
-                *sp[g] = make_uint4(pack_bf16x2(f[8 * g], f[8 * g + 1]), pack_bf16x2(f[8 * g + 2], f[8 * g + 3]),
-                                    pack_bf16x2(f[8 * g + 4], f[8 * g + 5]), pack_bf16x2(f[8 * g + 6], f[8 * g + 7]));
-            }
-          } else
-          for (int c0 = half * 32; c0 < cend; c0 += 16) {
-            uint32_t v[16];
-            tmem_ld_x16(taddr + j * 64 + c0, v);
-            tmem_ld_wait();
-            const int ch = nt * p.block_n + j * 64 + c0;
-            if (row < box_rows) {
-              float f[16];
-#pragma unroll
-              for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
-              if (p.bias && ch < p.cout) {
-                const float4* bp = reinterpret_cast<const float4*>(p.bias + ch);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  const float4 b4 = __ldg(bp + i);
-                  f[4 * i] += b4.x; f[4 * i + 1] += b4.y; f[4 * i + 2] += b4.z; f[4 * i + 3] += b4.w;
-                }
-              }
-              if (p.relu) {
-#pragma unroll
-                for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
-              }
-              const int cc = c0 >> 3;
-              uint4* s0 = reinterpret_cast<uint4*>(sb + row * 128 + (((cc) ^ (row & 7)) << 4));
-              uint4* s1 = reinterpret_cast<uint4*>(sb + row * 128 + (((cc + 1) ^ (row & 7)) << 4));
-              if (p.aux_mode == 3) {
-                const uint32_t bits = dropout_bits16(e_row + (unsigned long long)ch, rng_seed, rng_off);
-#pragma unroll
-                for (int i = 0; i < 16; ++i) f[i] = ((bits >> i) & 1u) ? f[i] * 2.f : 0.f;
-              } else if (p.aux_mode) {
-                const uint4 a0 = *s0, a1 = *s1;
-                const uint32_t au[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  const float lo = bf16lo(au[i]), hi = bf16hi(au[i]);
-                  if (p.aux_mode == 1) {
-                    f[2 * i] = lo > 0.f ? f[2 * i] : 0.f;
-                    f[2 * i + 1] = hi > 0.f ? f[2 * i + 1] : 0.f;
-                  } else {
-                    f[2 * i] *= lo;
-                    f[2 * i + 1] *= hi;
-                  }
-                }
-              }
-              *s0 = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
-                               pack_bf16x2(f[6], f[7]));
-              *s1 = make_uint4(pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]), pack_bf16x2(f[12], f[13]),
-                               pack_bf16x2(f[14], f[15]));
-            }
-          }
-          fence_proxy_async_smem();
-          named_bar_sync(2, 256);
-          if (leader) {
-            tma_store_4d(&tmO, sb, nt * p.block_n + j * 64, w0, h0, n0);
-            bulk_commit();
-          }
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) { if constexpr (cta2) mbar_arrive_cluster(&tempty_bar[buf], 0); else mbar_arrive(&tempty_bar[buf]); }
-      }
-      if (leader) bulk_wait_all();
+      epilogue_tma<cta2>(ea, &tmO, &tmX, smem + (size_t)p.stages * stage_bytes, aux_bar, tfull_bar, tempty_bar, tmem,
+                         my_tiles, tile_of);
     } else {
       const int q = warp & 3, half = (warp - 2) >> 2;
       const int row = q * 32 + lane;
@@ -488,7 +342,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) { if constexpr (cta2) mbar_arrive_cluster(&tempty_bar[buf], 0); else mbar_arrive(&tempty_bar[buf]); }
+        if (lane == 0) { if constexpr (cta2) mbar_arrive_cluster_relaxed(&tempty_bar[buf], 0); else mbar_arrive(&tempty_bar[buf]); }
       }
     }
   }
@@ -571,6 +425,7 @@ int conv_fprop(const Act& x, const void* wk, int R, int S, int pad, const Act& o
   p.nbuf = 4;
   if (tma_epi && (kSmemBudget - 4 * kEpiBuf) / stage_bytes < 4) p.nbuf = 2;  // keep >= 4 operand stages
   if (tma_epi && (epi.epi_bufs == 2 || epi.epi_bufs == 4 || epi.epi_bufs == 8)) p.nbuf = epi.epi_bufs;
+  p.nbuf_log2 = p.nbuf == 8 ? 3 : (p.nbuf == 4 ? 2 : 1);
   const int ring = tma_epi ? p.nbuf * kEpiBuf : 0;
   p.stages = (kSmemBudget - ring) / stage_bytes;
   if (p.stages > kMaxStages) p.stages = kMaxStages;
@@ -780,7 +635,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) { if constexpr (cta2) mbar_arrive_cluster(&tempty_bar[buf], 0); else mbar_arrive(&tempty_bar[buf]); }
+      if (lane == 0) { if constexpr (cta2) mbar_arrive_cluster_relaxed(&tempty_bar[buf], 0); else mbar_arrive(&tempty_bar[buf]); }
     }
   }
   tc_fence_before();

@@ -416,8 +416,11 @@ struct Net {
   }
 
   // ---- backward: d_head / d_rf (bf16, written by loss() or by the caller) -> parameter gradients in g32 (+=)
-  int backward(cudaStream_t st) {
+  // stage: -1 = everything; 0 = refine + heads + conv4 block (gradients of bucket 0 complete, see grad_bucket);
+  // 1 = conv3 .. conv1.  The split lets a data-parallel caller all-reduce bucket 0 while stage 1 still computes.
+  int backward(cudaStream_t st, int stage = -1) {
     if (!train || !forward_done) return DBX_ERR_STATE;
+    if (stage < -1 || stage > 1) return DBX_ERR_ARG;
     if (dgrad_pending) { DBX_TRY((int)cudaStreamWaitEvent(st, ev_join, 0)); dgrad_pending = false; }
     if (dgrad_stale) DBX_TRY(refresh_dgrad(st));
     const int h2 = H / 2, w2 = W / 2, h4 = H / 4, w4 = W / 4, h8 = H / 8, w8 = W / 8;
@@ -437,6 +440,7 @@ struct Net {
     Act d_p2 = act("d_p2", h4, w4, 128), d_a22 = act("d_a22", h2, w2, 128), d_a21 = act("d_a21", h2, w2, 128);
     Act d_p1 = act("d_p1", h2, w2, 64), d_a12 = act("d_a12", H, W, 64), d_a11 = act("d_a11", H, W, 64);
 
+    if (stage != 1) {
     if (variant >= 1) {
       Act rp = act("rp", h8, w8, 64), r1 = act("r1", h8 - 2, w8 - 2, 64);
       Act rup = act("rup", h4, w4, 64);
@@ -476,6 +480,8 @@ struct Net {
     DBX_TRY(dgrad(d_a42, "conv4_2", 3, 1, d_a41, &a41, st));
     DBX_TRY(wgrad(p3, d_a41, "conv4_1", 3, 1, st));
     DBX_TRY(dgrad(d_a41, "conv4_1", 3, 1, d_p3, nullptr, st));
+    if (stage == 0) return join_side(st);
+    }
     // conv3 block: pool3 backward + the concat branch of conv3_4, then ReLU mask
     DBX_K("pool_bwd", 0.0, maxpool2x2_bwd(a34, d_p3, &d_fus_34, d_a34, st));
     DBX_TRY(wgrad(a32, d_a34, "conv3_4", 3, 1, st));
@@ -610,6 +616,32 @@ int dbx_net_loss(void* handle, const float* bbox, const float* vertices, const f
 int dbx_net_backward(void* handle, void* stream) {
   if (!handle) return DBX_ERR_ARG;
   return ((Net*)handle)->backward((cudaStream_t)stream);
+}
+int dbx_net_backward_stage(void* handle, int stage, void* stream) {
+  if (!handle || stage < 0 || stage > 1) return DBX_ERR_ARG;
+  return ((Net*)handle)->backward((cudaStream_t)stream, stage);
+}
+int dbx_net_join(void* handle, void* stream) {
+  if (!handle) return DBX_ERR_ARG;
+  Net* n = (Net*)handle;
+  if (n->dgrad_pending) {
+    n->dgrad_pending = false;
+    return (int)cudaStreamWaitEvent((cudaStream_t)stream, n->ev_join, 0);
+  }
+  return DBX_OK;
+}
+int dbx_net_grad_bucket(void* handle, int bucket, long long* first, long long* count) {
+  if (!handle || !first || !count) return DBX_ERR_ARG;
+  Net* n = (Net*)handle;
+  if (!n->train) return DBX_ERR_STATE;
+  const long long split = (long long)n->groups[n->group_id("conv4_1")].w_off;
+  const long long bias0 = (long long)n->groups[0].b_off;
+  switch (bucket) {
+    case 0: *first = split; *count = bias0 - split; return DBX_OK;            // conv4_1 .. heads (+ refine) filters
+    case 1: *first = 0; *count = split; return DBX_OK;                         // conv1_1 .. conv3_4 filters
+    case 2: *first = bias0; *count = (long long)n->flat_n - bias0; return DBX_OK;  // every bias
+    default: return DBX_ERR_ARG;
+  }
 }
 int dbx_net_zero_grad(void* handle, void* stream) {
   if (!handle) return DBX_ERR_ARG;

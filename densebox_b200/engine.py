@@ -136,6 +136,20 @@ class NetEngine:
     def backward(self):
         check(lib().dbx_net_backward(self.h, stream_ptr()), "net_backward")
 
+    def backward_stage(self, stage):
+        """Half of backward(): 0 = refine + heads + conv4 block, 1 = conv3 .. conv1 (data-parallel overlap)."""
+        check(lib().dbx_net_backward_stage(self.h, c_int(stage), stream_ptr()), "net_backward_stage")
+
+    def join(self):
+        check(lib().dbx_net_join(self.h, stream_ptr()), "net_join")
+
+    def grad_bucket(self, bucket):
+        """View of g32 holding gradient bucket 0 (conv4..heads filters), 1 (conv1..conv3 filters) or 2 (biases)."""
+        first, count = ctypes.c_longlong(0), ctypes.c_longlong(0)
+        check(lib().dbx_net_grad_bucket(self.h, c_int(bucket), ctypes.byref(first), ctypes.byref(count)),
+              "net_grad_bucket")
+        return self.flat_grads()[first.value:first.value + count.value]
+
     def zero_grad(self):
         check(lib().dbx_net_zero_grad(self.h, stream_ptr()), "net_zero_grad")
 

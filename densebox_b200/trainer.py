@@ -3,9 +3,12 @@ step: H2D of the batch, forward, fused loss, hand-written backward, gradient all
 
 The reference's loop crosses the host/device boundary 7+ times per step and synchronises twice; here nothing leaves
 the GPU between the input copy and the scalar loss.  With `use_cuda_graph=True` forward+loss+backward and the SGD
-update are replayed as two CUDA graphs; the NCCL all-reduce of the flat gradient buffer sits between them.
+update are replayed as CUDA graphs.
 Data parallel: one process per GPU, batch sharded by rank, gradient SUM all-reduce (the loss is a sum,
 DenseBox.py:2917), and the negative quota uses the batch-GLOBAL positive count (:2864-2868) via a 1-int all-reduce.
+Both exchanges are hidden behind compute: the count all-reduce runs while the forward graph replays (only the loss
+needs it), and the backward pass is cut after the conv4 block so that the all-reduce of the conv4/heads filters
+(87 % of the gradient bytes) overlaps the conv3..conv1 half of backward; the small second bucket follows.
 """
 import ctypes
 
@@ -43,6 +46,7 @@ class DenseBoxTrainer:
         self.use_labels = False
         self.use_graph = use_cuda_graph
         self._graph_fb = self._graph_sgd = None
+        self._graphs_dp = None  # (forward, loss + backward stage 0, backward stage 1) when world > 1
         self._graph_lr = None
         self._rng = self.eng.buffer("rng", torch.int64)
         drop_elems = self.eng.buffer("drop", torch.bfloat16).numel()
@@ -75,13 +79,49 @@ class DenseBoxTrainer:
     def _fwd_loss_bwd(self):
         e = self.eng
         e.forward(self.x, dropout_mode=3 if self.dropout else 0)  # Philox in the epilogues, state in the rng region
-        ll, ld, lm = self.lambdas
-        e.loss(self.bbox, vertices=self.vertices if self.variant != "densebox" else None,
-               labels=self.labels if self.use_labels else None, rand_idx=self.rand,
-               lm_rand_idx=self.lm_rand if self.variant != "densebox" else None, lambda_loc=ll, lambda_det=ld,
-               lambda_lm=lm, global_pos_dev=self.gpos if self.world > 1 else None,
-               global_batch=self.B * self.world if self.world > 1 else -1, clamp_lm=self.use_labels)
+        self._loss()
         e.backward()
+
+    def _loss(self):
+        ll, ld, lm = self.lambdas
+        self.eng.loss(self.bbox, vertices=self.vertices if self.variant != "densebox" else None,
+                      labels=self.labels if self.use_labels else None, rand_idx=self.rand,
+                      lm_rand_idx=self.lm_rand if self.variant != "densebox" else None, lambda_loc=ll, lambda_det=ld,
+                      lambda_lm=lm, global_pos_dev=self.gpos if self.world > 1 else None,
+                      global_batch=self.B * self.world if self.world > 1 else -1, clamp_lm=self.use_labels)
+
+    def _step_dp(self, graph_ok):
+        """forward | loss + backward(heads, conv4) | backward(conv3..conv1) with the two exchanges overlapped."""
+        e, dist = self.eng, torch.distributed
+
+        def fwd():
+            e.forward(self.x, dropout_mode=3 if self.dropout else 0)
+            e.join()
+
+        def lb0():
+            self._loss()
+            e.backward_stage(0)
+
+        parts = (fwd, lb0, lambda: e.backward_stage(1))
+        if graph_ok and self._graphs_dp is None:  # capture before any collective of this step is in flight
+            self._graphs_dp = []
+            for fn in parts:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                    fn()
+                self._graphs_dp.append(g)
+        check(lib().dbx_count_positives(ptr(self.bbox), ptr(self.labels if self.use_labels else None),
+                                        c_int(self.B), ptr(self.gpos), stream_ptr()), "count_positives")
+        w_count = dist.all_reduce(self.gpos, group=self.pg, async_op=True)
+        run = [g.replay for g in self._graphs_dp] if graph_ok else parts
+        run[0]()
+        w_count.wait()
+        run[1]()
+        works = [dist.all_reduce(e.grad_bucket(0), group=self.pg, async_op=True)]  # SUM: the loss is a sum (:2917)
+        run[2]()
+        works += [dist.all_reduce(e.grad_bucket(b), group=self.pg, async_op=True) for b in (1, 2)]
+        for w in works:
+            w.wait()
 
     def step(self, x, bbox, vertices=None, labels=None, rand_neg_idx=None, lm_rand_neg_idx=None):
         """x [B,3,240,240] fp32 (host pinned or device), labels in 60-space. Returns the loss as a 0-dim CUDA tensor
@@ -106,25 +146,22 @@ class DenseBoxTrainer:
         if self.dropout:  # a fresh mask per step: advance the Philox counter offset (device side, graph safe)
             self._rng[0] = self.seed
             self._rng[1] = self.step_no * self._rng_stride
-        if self.world > 1:
-            check(lib().dbx_count_positives(ptr(self.bbox), ptr(self.labels if self.use_labels else None),
-                                            c_int(self.B), ptr(self.gpos), stream_ptr()), "count_positives")
-            torch.distributed.all_reduce(self.gpos, group=self.pg)
         graph_ok = self.use_graph and self.step_no >= 1  # step 0 runs eagerly (one-time inits, SGD first-step flag)
-        if graph_ok and self._graph_fb is None:
-            self._graph_fb = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self._graph_fb):
-                self._fwd_loss_bwd()
-        if graph_ok:
-            self._graph_fb.replay()
-        else:
-            self._fwd_loss_bwd()
         if self.world > 1:
-            torch.distributed.all_reduce(e.flat_grads(), group=self.pg)  # SUM: the loss is a sum over the batch
+            self._step_dp(graph_ok)
+        else:
+            if graph_ok and self._graph_fb is None:
+                self._graph_fb = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self._graph_fb):
+                    self._fwd_loss_bwd()
+            if graph_ok:
+                self._graph_fb.replay()
+            else:
+                self._fwd_loss_bwd()
         if graph_ok and (self._graph_sgd is None or self._graph_lr != self.lr):
             self._graph_sgd = torch.cuda.CUDAGraph()
             self._graph_lr = self.lr
-            with torch.cuda.graph(self._graph_sgd):
+            with torch.cuda.graph(self._graph_sgd, capture_error_mode="thread_local"):
                 e.sgd_step(self.lr, self.momentum, self.weight_decay)
             # capture does not execute: fall through to replay
         if graph_ok:

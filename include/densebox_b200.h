@@ -130,6 +130,15 @@ int dbx_net_loss(void* handle, const float* bbox, const float* vertices, const f
 
 /* loss.backward() — DenseBox.py:2925: consumes "d_head"/"d_rf", accumulates (+=) parameter gradients into "g32". */
 int dbx_net_backward(void* handle, void* stream);
+/* The same backward pass in two halves for data-parallel callers (the reference is single-device, the
+ * autograd graph of :2925 is simply cut after conv4_1): stage 0 = refine branch + heads + conv4 block, stage 1 =
+ * conv3 .. conv1.  After stage 0 the gradients of bucket 0 are final, so their all-reduce overlaps stage 1.
+ * dbx_net_grad_bucket: element range [first, first+count) of "g32" — bucket 0 = filters conv4_1..heads(+refine),
+ * 1 = filters conv1_1..conv3_4, 2 = every bias.  dbx_net_join: make `stream` wait for the filter re-layout that
+ * dbx_net_forward forked onto the engine's side stream (needed when forward is captured into its own CUDA graph). */
+int dbx_net_backward_stage(void* handle, int stage, void* stream);
+int dbx_net_grad_bucket(void* handle, int bucket, long long* first, long long* count);
+int dbx_net_join(void* handle, void* stream);
 int dbx_net_zero_grad(void* handle, void* stream);                       /* optimizer.zero_grad() :2858 */
 /* optimizer.step() — torch.optim.SGD(momentum, weight_decay) :2821-2824, :2926; also clears g32 and refreshes the
  * bf16 filters. */
