@@ -6,7 +6,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libdensebox_b200.so")
+# DBX_LIB: A/B measurements of two builds in one process run (tools/ only); the default is the in-tree build
+LIB_PATH = os.environ.get("DBX_LIB") or os.path.join(_HERE, "csrc", "libdensebox_b200.so")
 _lib = None
 
 

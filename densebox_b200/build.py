@@ -36,17 +36,20 @@ def _digest():
     return h.hexdigest()
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, out=None, extra_flags=()):
+    """out / extra_flags: build a VARIANT of the library somewhere else (tools/ab A/B measurements)."""
+    variant = out is not None
+    lib = out or LIB
     stamp = os.path.join(CSRC, ".build_stamp")
     dig = _digest()
-    if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == dig:
+    if not variant and not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == dig:
         return LIB
-    objdir = os.path.join(CSRC, "build")
+    objdir = os.path.join(CSRC, "build", os.path.basename(lib) + ".obj") if variant else os.path.join(CSRC, "build")
     os.makedirs(objdir, exist_ok=True)
 
     def cc(src):
         obj = os.path.join(objdir, src[:-3] + ".o")
-        cmd = [NVCC] + FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [NVCC] + FLAGS + list(extra_flags) + ["-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, r.stdout, r.stderr))
@@ -58,14 +61,18 @@ def build(force=False, verbose=False):
         for _, log in results:
             sys.stderr.write(log)
     objs = [o for o, _ in results]
-    cmd = [NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + ["-lpthread", "-ldl"]
+    cmd = [NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", lib] + objs + ["-lpthread", "-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
-    with open(stamp, "w") as f:
-        f.write(dig)
-    return LIB
+    if not variant:
+        with open(stamp, "w") as f:
+            f.write(dig)
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose=True))
+    # python -m densebox_b200.build [--force] [--out PATH] [-DNAME=VALUE ...]
+    _out = sys.argv[sys.argv.index("--out") + 1] if "--out" in sys.argv else None
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, out=_out,
+                extra_flags=[a for a in sys.argv[1:] if a.startswith("-D")]))

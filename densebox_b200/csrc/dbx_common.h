@@ -56,6 +56,9 @@ struct ConvEpilogue {
   int out_fp32 = 0;            // output element type: 0 bf16, 1 fp32
   int force_cta2 = -1;         // -1 = auto, 0 = never pair CTAs (tcgen05.mma.cta_group::2)
   int epi_bufs = 0;            // 0 = auto; 2/4/8 epilogue staging boxes (short-K GEMMs with a mask want a deep ring)
+  float* colsum = nullptr;     // fp32 [cout] or null: colsum[c] += sum over pixels of out[.., c] (as stored, bf16-rounded).
+                               // A data-gradient launch uses it to produce the bias gradient of the layer below
+                               // in its own epilogue instead of re-reading dY from HBM; requires bias == nullptr.
 };
 
 // out[n,oh,ow,:] = epi( sum_{r,s,ci} x[n,oh+r-pad,ow+s-pad,ci] * wk[co][(r*S+s)*Cin+ci] )
@@ -74,9 +77,10 @@ int conv_wgrad(const Act& x, const Act& dy, int R, int S, int pad, float* dw, in
 // ---- HBM-bound kernels (dbx_elementwise.cu)
 int im2col3x3_c3(const float* x, void* out, int N, int H, int W, int write_pad, cudaStream_t st);
 int maxpool2x2_fwd(const Act& y, const Act& o, cudaStream_t st);
-int maxpool2x2_bwd(const Act& y, const Act& dp, const Act* add, const Act& dy, cudaStream_t st);
+// db (optional, both): db[c] += column sums of the gradient written (bias gradient of the conv that produced y)
+int maxpool2x2_bwd(const Act& y, const Act& dp, const Act* add, const Act& dy, cudaStream_t st, float* db = nullptr);
 int upsample_bilinear_fwd(const Act& in, const Act& out, cudaStream_t st);
-int upsample_bilinear_bwd(const Act& dout, const Act* relu_y, const Act& din, cudaStream_t st);
+int upsample_bilinear_bwd(const Act& dout, const Act* relu_y, const Act& din, cudaStream_t st, float* db = nullptr);
 int colsum(const Act& dy, float* db, cudaStream_t st);
 int pack_weights(const float* src, int co, int ci, int R, int S, long s_co, long s_ci, long s_r, long s_s, void* dstK,
                  long ldK, long rowK, long kK, int cin_pad, void* dstD, long ldD, long rowD, long kD, int cout_pad,

@@ -31,6 +31,7 @@ struct HaloParams {
   uint32_t idesc, tmem_cols;
   const float* bias;
   int relu, aux_mode;
+  float* colsum; int csum_off;  // fused bias gradient of the layer below (see ConvEpilogue::colsum)
 };
 
 __global__ void __launch_bounds__(kHaloThreads, 1)
@@ -66,6 +67,8 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     fence_barrier_init();
   }
   if (warp == 1) { tmem_alloc(&tmem_base_s, p.tmem_cols); tmem_relinquish(); }
+  float* csum = p.colsum ? reinterpret_cast<float*>(smem + p.csum_off) : nullptr;
+  if (csum) for (int c = threadIdx.x; c < p.cout; c += kHaloThreads) csum[c] = 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -190,6 +193,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     ea.block_n = p.block_n; ea.nsb = p.nsb; ea.nbuf_log2 = p.nbuf_log2;
     ea.tw = 8; ea.th = 16; ea.box_rows = 128;
     ea.out_W = 0; ea.out_H = 0; ea.rng = nullptr; ea.rng_channels = 0;
+    ea.csum = csum;
     const int my_tiles = (int)blockIdx.x < total ? (total - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
     auto tile_of = [&](int it, int& nt, int& w0, int& h0, int& n0) {
       const int t = (int)blockIdx.x + it * (int)gridDim.x;
@@ -201,6 +205,8 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
   tc_fence_before();
   __syncthreads();
+  if (csum)
+    for (int c = threadIdx.x; c < p.cout; c += kHaloThreads) { const float v = csum[c]; if (v != 0.f) atomicAdd(p.colsum + c, v); }
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem, p.tmem_cols); }
 }
 
@@ -215,6 +221,8 @@ int conv3x3_halo(const Act& x, const void* wk, const Act& out, const ConvEpilogu
   if (!x.ptr || !wk || !out.ptr || epi.out_fp32) return DBX_ERR_ARG;
   if (x.C % 64 || x.C > 128 || out.C % 64 || out.H != x.H || out.W != x.W || out.N != x.N) return DBX_ERR_ARG;
   if (epi.aux_mode && (!epi.aux || epi.aux_cs % 8 || epi.aux_coff % 8)) return DBX_ERR_ARG;
+  if (epi.colsum && epi.bias) return DBX_ERR_ARG;
+  const int csum_bytes = epi.colsum ? (out.C * 4 + 1023) / 1024 * 1024 : 0;
   HaloParams p{};
   p.block_n = out.C >= 128 ? 128 : 64;
   p.tiles_w = (out.W + 7) / 8; p.tiles_h = (out.H + 15) / 16;
@@ -231,21 +239,23 @@ int conv3x3_halo(const Act& x, const void* wk, const Act& out, const ConvEpilogu
   p.nbuf = 2;
   if (p.resident) {
     p.b_slots = 0;
-    int avail = kHaloSmem - kb_per_tile * b_tile;
+    int avail = kHaloSmem - kb_per_tile * b_tile - csum_bytes;
     p.nbuf = 4; p.a_slots = (avail - p.nbuf * kEpiBox) / kSBox;
     if (p.a_slots < 4) { p.nbuf = 2; p.a_slots = (avail - p.nbuf * kEpiBox) / kSBox; }
     if (p.a_slots > kMaxASlots) p.a_slots = kMaxASlots;
     if (p.a_slots < 3) return DBX_ERR_ARG;
   } else {
     p.a_slots = 6;
-    int avail = kHaloSmem - p.a_slots * kSBox - p.nbuf * kEpiBox;
+    int avail = kHaloSmem - p.a_slots * kSBox - p.nbuf * kEpiBox - csum_bytes;
     p.b_slots = avail / b_tile;
     if (p.b_slots > kMaxBSlots) p.b_slots = kMaxBSlots;
     if (p.b_slots < 3) return DBX_ERR_ARG;
   }
   p.nbuf_log2 = p.nbuf == 8 ? 3 : (p.nbuf == 4 ? 2 : 1);
-  const size_t smem = (size_t)p.a_slots * kSBox + (size_t)(p.resident ? kb_per_tile : p.b_slots) * b_tile +
-                      (size_t)p.nbuf * kEpiBox + 1024;
+  p.colsum = epi.colsum;
+  p.csum_off = (int)((size_t)p.a_slots * kSBox + (size_t)(p.resident ? kb_per_tile : p.b_slots) * b_tile +
+                     (size_t)p.nbuf * kEpiBox);
+  const size_t smem = (size_t)p.csum_off + csum_bytes + 1024;
   if (smem > (size_t)kHaloSmem + 1024) return DBX_ERR_ARG;
   p.idesc = umma_idesc_bf16(128, p.block_n, 0, 0);
   p.tmem_cols = 2 * p.block_n <= 128 ? 128 : 256;

@@ -5,6 +5,7 @@
 // All kernels move 16-byte (8 x bf16) vectors, one vector per thread, channel-fastest so that warps are coalesced.
 #include "dbx_common.h"
 #include "dbx_ptx.cuh"
+#include <stdlib.h>
 
 namespace dbx {
 
@@ -93,56 +94,98 @@ int maxpool2x2_fwd(const Act& y, const Act& o, cudaStream_t st) {
   return (int)cudaGetLastError();
 }
 
-// dy = relu'(y) * ( maxpool_bwd(dp)  [+ add] ): gradient goes to the FIRST maximum of each window in scan order
-// (torch max_pool2d semantics), then the ReLU mask of the producing conv (y > 0) is applied.
-__global__ void maxpool2x2_bwd_kernel(Act y, Act dp, Act add, int has_add, Act dy) {
-  const int cc = dp.C / 8;
-  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const size_t total = (size_t)dp.N * dp.H * dp.W * cc;
-  if (idx >= total) return;
-  const int c = (int)(idx % cc) * 8;
-  const size_t pix = idx / cc;
-  const int ox = (int)(pix % dp.W), oy = (int)((pix / dp.W) % dp.H), n = (int)(pix / ((size_t)dp.W * dp.H));
-  float v[4][8], g[8], o[4][8];
-  unpack8(ldg16(at(y, n, 2 * oy, 2 * ox, c)), v[0]);
-  unpack8(ldg16(at(y, n, 2 * oy, 2 * ox + 1, c)), v[1]);
-  unpack8(ldg16(at(y, n, 2 * oy + 1, 2 * ox, c)), v[2]);
-  unpack8(ldg16(at(y, n, 2 * oy + 1, 2 * ox + 1, c)), v[3]);
-  unpack8(ldg16(at(dp, n, oy, ox, c)), g);
-  if (has_add) {
-    unpack8(ldg16(at(add, n, 2 * oy, 2 * ox, c)), o[0]);
-    unpack8(ldg16(at(add, n, 2 * oy, 2 * ox + 1, c)), o[1]);
-    unpack8(ldg16(at(add, n, 2 * oy + 1, 2 * ox, c)), o[2]);
-    unpack8(ldg16(at(add, n, 2 * oy + 1, 2 * ox + 1, c)), o[3]);
-  } else {
+// Block-level fold of per-thread channel partials into db (bias gradient): thread t owns channels 8 (t % cc) .. + 7.
+__device__ __forceinline__ void fold_bias_partials(const float* acc, int cc, float* __restrict__ db, float* red) {
+  // red: [blockDim.x][8] floats of shared memory
 #pragma unroll
-    for (int k = 0; k < 4; ++k)
-#pragma unroll
-      for (int j = 0; j < 8; ++j) o[k][j] = 0.f;
+  for (int j = 0; j < 8; ++j) red[threadIdx.x * 8 + j] = acc[j];
+  __syncthreads();
+  const int C = cc * 8, reps = (int)blockDim.x / cc;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.f;
+    for (int k = 0; k < reps; ++k) s += red[(k * cc + c / 8) * 8 + (c & 7)];
+    if (s != 0.f) atomicAdd(db + c, s);
   }
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    int arg = 0; float m = v[0][j];
-    if (v[1][j] > m) { m = v[1][j]; arg = 1; }
-    if (v[2][j] > m) { m = v[2][j]; arg = 2; }
-    if (v[3][j] > m) { m = v[3][j]; arg = 3; }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      float r = o[k][j] + (k == arg ? g[j] : 0.f);
-      o[k][j] = v[k][j] > 0.f ? r : 0.f;
-    }
-  }
-  *reinterpret_cast<uint4*>(at(dy, n, 2 * oy, 2 * ox, c)) = pack8(o[0]);
-  *reinterpret_cast<uint4*>(at(dy, n, 2 * oy, 2 * ox + 1, c)) = pack8(o[1]);
-  *reinterpret_cast<uint4*>(at(dy, n, 2 * oy + 1, 2 * ox, c)) = pack8(o[2]);
-  *reinterpret_cast<uint4*>(at(dy, n, 2 * oy + 1, 2 * ox + 1, c)) = pack8(o[3]);
 }
 
-int maxpool2x2_bwd(const Act& y, const Act& dp, const Act* add, const Act& dy, cudaStream_t st) {
+// dy = relu'(y) * ( maxpool_bwd(dp)  [+ add] ): gradient goes to the FIRST maximum of each window in scan order
+// (torch max_pool2d semantics), then the ReLU mask of the producing conv (y > 0) is applied.
+// db (optional): db[c] += sum over pixels of dy[.., c] as stored — the bias gradient of the conv that produced y,
+// folded here so that dy is not read from HBM a second time.  Threads keep their channel vector across the
+// grid-stride loop (the stride is a multiple of C/8).
+__global__ void __launch_bounds__(256) maxpool2x2_bwd_kernel(Act y, Act dp, Act add, int has_add, Act dy,
+                                                             float* __restrict__ db) {
+  __shared__ float red[256 * 8];
+  const int cc = dp.C / 8;
+  const size_t total = (size_t)dp.N * dp.H * dp.W * cc;
+  float bsum[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) bsum[j] = 0.f;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % cc) * 8;
+    const size_t pix = idx / cc;
+    const int ox = (int)(pix % dp.W), oy = (int)((pix / dp.W) % dp.H), n = (int)(pix / ((size_t)dp.W * dp.H));
+    float v[4][8], g[8], o[4][8];
+    unpack8(ldg16(at(y, n, 2 * oy, 2 * ox, c)), v[0]);
+    unpack8(ldg16(at(y, n, 2 * oy, 2 * ox + 1, c)), v[1]);
+    unpack8(ldg16(at(y, n, 2 * oy + 1, 2 * ox, c)), v[2]);
+    unpack8(ldg16(at(y, n, 2 * oy + 1, 2 * ox + 1, c)), v[3]);
+    unpack8(ldg16(at(dp, n, oy, ox, c)), g);
+    if (has_add) {
+      unpack8(ldg16(at(add, n, 2 * oy, 2 * ox, c)), o[0]);
+      unpack8(ldg16(at(add, n, 2 * oy, 2 * ox + 1, c)), o[1]);
+      unpack8(ldg16(at(add, n, 2 * oy + 1, 2 * ox, c)), o[2]);
+      unpack8(ldg16(at(add, n, 2 * oy + 1, 2 * ox + 1, c)), o[3]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[k][j] = 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      int arg = 0; float m = v[0][j];
+      if (v[1][j] > m) { m = v[1][j]; arg = 1; }
+      if (v[2][j] > m) { m = v[2][j]; arg = 2; }
+      if (v[3][j] > m) { m = v[3][j]; arg = 3; }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float r = o[k][j] + (k == arg ? g[j] : 0.f);
+        o[k][j] = v[k][j] > 0.f ? r : 0.f;
+      }
+    }
+    uint4 q[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) q[k] = pack8(o[k]);
+    *reinterpret_cast<uint4*>(at(dy, n, 2 * oy, 2 * ox, c)) = q[0];
+    *reinterpret_cast<uint4*>(at(dy, n, 2 * oy, 2 * ox + 1, c)) = q[1];
+    *reinterpret_cast<uint4*>(at(dy, n, 2 * oy + 1, 2 * ox, c)) = q[2];
+    *reinterpret_cast<uint4*>(at(dy, n, 2 * oy + 1, 2 * ox + 1, c)) = q[3];
+    if (db) {  // sum what was stored (bf16-rounded), like the stand-alone colsum kernel would
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float f[8];
+        unpack8(q[k], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) bsum[j] += f[j];
+      }
+    }
+  }
+  if (db) fold_bias_partials(bsum, cc, db, red);
+}
+
+int maxpool2x2_bwd(const Act& y, const Act& dp, const Act* add, const Act& dy, cudaStream_t st, float* db) {
   if (y.H != 2 * dp.H || y.W != 2 * dp.W || y.C != dp.C || dy.C != y.C || dy.H != y.H || dy.W != y.W || y.C % 8)
     return DBX_ERR_ARG;
-  const size_t total = (size_t)dp.N * dp.H * dp.W * (dp.C / 8);
-  maxpool2x2_bwd_kernel<<<grid_for(total, 256), 256, 0, st>>>(y, dp, add ? *add : y, add ? 1 : 0, dy);
+  const int cc = dp.C / 8;
+  const size_t total = (size_t)dp.N * dp.H * dp.W * cc;
+  if (db && (256 % cc) != 0) {  // threads could not keep their channels: separate pass
+    const int rc = maxpool2x2_bwd(y, dp, add, dy, st, nullptr);
+    return rc ? rc : colsum(dy, db, st);
+  }
+  int blocks = grid_for(total, 256);
+  if (blocks > 16 * num_sms()) blocks = 16 * num_sms();
+  maxpool2x2_bwd_kernel<<<blocks, 256, 0, st>>>(y, dp, add ? *add : y, add ? 1 : 0, dy, db);
   return (int)cudaGetLastError();
 }
 
@@ -160,86 +203,136 @@ __device__ __forceinline__ Lin lin_coord(int d, float scale, int in_size) {
   return r;
 }
 
-__global__ void upsample_fwd_kernel(Act in, Act out, float sh, float sw) {
+// One block per output row (n, oy): the row's vertical coordinates are hoisted, every thread walks (pixel, 8-channel
+// vector) pairs 256 apart so a warp stores 512 contiguous bytes per instruction, four vectors in flight per thread.
+__global__ void __launch_bounds__(256) upsample_fwd_kernel(Act in, Act out, float sh, float sw) {
   const int cc = out.C / 8;
-  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const size_t total = (size_t)out.N * out.H * out.W * cc;
-  if (idx >= total) return;
-  const int c = (int)(idx % cc) * 8;
-  const size_t pix = idx / cc;
-  const int ox = (int)(pix % out.W), oy = (int)((pix / out.W) % out.H), n = (int)(pix / ((size_t)out.W * out.H));
-  const Lin ly = lin_coord(oy, sh, in.H), lx = lin_coord(ox, sw, in.W);
-  float a[8], b[8], c0[8], d[8], o[8];
-  unpack8(ldg16(at(in, n, ly.i0, lx.i0, c)), a);
-  unpack8(ldg16(at(in, n, ly.i0, lx.i1, c)), b);
-  unpack8(ldg16(at(in, n, ly.i1, lx.i0, c)), c0);
-  unpack8(ldg16(at(in, n, ly.i1, lx.i1, c)), d);
+  const int oy = (int)(blockIdx.x % out.H), n = (int)(blockIdx.x / out.H);
+  const Lin ly = lin_coord(oy, sh, in.H);
+  const bf16* r0 = at(in, n, ly.i0, 0, 0);
+  const bf16* r1 = at(in, n, ly.i1, 0, 0);
+  bf16* orow = at(out, n, oy, 0, 0);
+  const int total = out.W * cc;
+  for (int v = threadIdx.x; v < total; v += 256) {
+    const int ox = v / cc, c = (v - ox * cc) * 8;
+    const Lin lx = lin_coord(ox, sw, in.W);
+    float a[8], b[8], c0[8], d[8], o[8];
+    unpack8(ldg16(r0 + (size_t)lx.i0 * in.cs + c), a);
+    unpack8(ldg16(r0 + (size_t)lx.i1 * in.cs + c), b);
+    unpack8(ldg16(r1 + (size_t)lx.i0 * in.cs + c), c0);
+    unpack8(ldg16(r1 + (size_t)lx.i1 * in.cs + c), d);
 #pragma unroll
-  for (int j = 0; j < 8; ++j)
-    o[j] = ly.l0 * (lx.l0 * a[j] + lx.l1 * b[j]) + ly.l1 * (lx.l0 * c0[j] + lx.l1 * d[j]);
-  *reinterpret_cast<uint4*>(at(out, n, oy, ox, c)) = pack8(o);
+    for (int j = 0; j < 8; ++j)
+      o[j] = ly.l0 * (lx.l0 * a[j] + lx.l1 * b[j]) + ly.l1 * (lx.l0 * c0[j] + lx.l1 * d[j]);
+    *reinterpret_cast<uint4*>(orow + (size_t)ox * out.cs + c) = pack8(o);
+  }
 }
 
 int upsample_bilinear_fwd(const Act& in, const Act& out, cudaStream_t st) {
   if (in.C != out.C || in.N != out.N || in.C % 8) return DBX_ERR_ARG;
   const float sh = out.H > 1 ? (float)(in.H - 1) / (float)(out.H - 1) : 0.f;
   const float sw = out.W > 1 ? (float)(in.W - 1) / (float)(out.W - 1) : 0.f;
-  const size_t total = (size_t)out.N * out.H * out.W * (out.C / 8);
-  upsample_fwd_kernel<<<grid_for(total, 256), 256, 0, st>>>(in, out, sh, sw);
+  upsample_fwd_kernel<<<out.N * out.H, 256, 0, st>>>(in, out, sh, sw);
   return (int)cudaGetLastError();
 }
 
 // din[n,iy,ix,:] = relu'(y) * sum over output pixels of their bilinear weight on (iy,ix) — a gather, so no atomics.
-__global__ void upsample_bwd_kernel(Act dout, Act y, int has_mask, Act din, float sh, float sw) {
+// One block per input row (n, iy).  The (output index, weight) lists of the row and of every input column are built
+// once per block in shared memory (a few entries each: an input pixel is touched by <= ceil(2/scale)+1 outputs per
+// axis), so the inner loop is loads and FMAs only; contributions are added in ascending (oy, ox) order.
+static constexpr int kUpMaxTaps = 8;
+static constexpr int kUpMaxW = 128;
+__global__ void __launch_bounds__(256) upsample_bwd_kernel(Act dout, Act y, int has_mask, Act din, float sh, float sw,
+                                                           float* __restrict__ db) {
+  __shared__ float red[256 * 8];
+  __shared__ int ycnt, yidx[kUpMaxTaps];
+  __shared__ float ywt[kUpMaxTaps];
+  __shared__ int xcnt[kUpMaxW], xidx[kUpMaxW][kUpMaxTaps];
+  __shared__ float xwt[kUpMaxW][kUpMaxTaps];
   const int cc = din.C / 8;
-  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const size_t total = (size_t)din.N * din.H * din.W * cc;
-  if (idx >= total) return;
-  const int c = (int)(idx % cc) * 8;
-  const size_t pix = idx / cc;
-  const int ix = (int)(pix % din.W), iy = (int)((pix / din.W) % din.H), n = (int)(pix / ((size_t)din.W * din.H));
-  int ylo = 0, yhi = dout.H - 1, xlo = 0, xhi = dout.W - 1;
-  if (sh > 0.f) { ylo = max(0, (int)floorf((iy - 1) / sh) - 1); yhi = min(dout.H - 1, (int)ceilf((iy + 1) / sh) + 1); }
-  if (sw > 0.f) { xlo = max(0, (int)floorf((ix - 1) / sw) - 1); xhi = min(dout.W - 1, (int)ceilf((ix + 1) / sw) + 1); }
-  float acc[8];
+  const int iy = (int)(blockIdx.x % din.H), n = (int)(blockIdx.x / din.H);
+  if (threadIdx.x == 0) {
+    int k = 0;
+    for (int oy = 0; oy < dout.H; ++oy) {
+      const Lin l = lin_coord(oy, sh, din.H);
+      const float w = (l.i0 == iy ? l.l0 : 0.f) + (l.i1 == iy ? l.l1 : 0.f);
+      if (w != 0.f && k < kUpMaxTaps) { yidx[k] = oy; ywt[k] = w; ++k; }
+    }
+    ycnt = k;
+  }
+  for (int ix = threadIdx.x; ix < din.W; ix += 256) {
+    int k = 0;
+    for (int ox = 0; ox < dout.W; ++ox) {
+      const Lin l = lin_coord(ox, sw, din.W);
+      const float w = (l.i0 == ix ? l.l0 : 0.f) + (l.i1 == ix ? l.l1 : 0.f);
+      if (w != 0.f && k < kUpMaxTaps) { xidx[ix][k] = ox; xwt[ix][k] = w; ++k; }
+    }
+    xcnt[ix] = k;
+  }
+  __syncthreads();
+  const int total = din.W * cc;
+  const int ny = ycnt;
+  float bsum[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-  for (int oy = ylo; oy <= yhi; ++oy) {
-    const Lin ly = lin_coord(oy, sh, din.H);
-    const float wy = (ly.i0 == iy ? ly.l0 : 0.f) + (ly.i1 == iy ? ly.l1 : 0.f);
-    if (wy == 0.f) continue;
-    for (int ox = xlo; ox <= xhi; ++ox) {
-      const Lin lx = lin_coord(ox, sw, din.W);
-      const float wx = (lx.i0 == ix ? lx.l0 : 0.f) + (lx.i1 == ix ? lx.l1 : 0.f);
-      if (wx == 0.f) continue;
-      float g[8];
-      unpack8(ldg16(at(dout, n, oy, ox, c)), g);
-      const float w = wy * wx;
+  for (int j = 0; j < 8; ++j) bsum[j] = 0.f;
+  for (int v = threadIdx.x; v < total; v += 256) {
+    const int ix = v / cc, c = (v - ix * cc) * 8;
+    const int nx = xcnt[ix];
+    float acc[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] += w * g[j];
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int a = 0; a < ny; ++a) {
+      const bf16* row = at(dout, n, yidx[a], 0, c);
+      const float wy = ywt[a];
+      for (int b = 0; b < nx; ++b) {
+        float g[8];
+        unpack8(ldg16(row + (size_t)xidx[ix][b] * dout.cs), g);
+        const float w = wy * xwt[ix][b];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += w * g[j];
+      }
+    }
+    if (has_mask) {
+      float m[8];
+      unpack8(ldg16(at(y, n, iy, ix, c)), m);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = m[j] > 0.f ? acc[j] : 0.f;
+    }
+    const uint4 q = pack8(acc);
+    *reinterpret_cast<uint4*>(at(din, n, iy, ix, c)) = q;
+    if (db) {  // bias gradient of the conv that produced y: sum of what was stored (256 % (C/8) == 0: fixed channels)
+      float f[8];
+      unpack8(q, f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) bsum[j] += f[j];
     }
   }
-  if (has_mask) {
-    float m[8];
-    unpack8(ldg16(at(y, n, iy, ix, c)), m);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = m[j] > 0.f ? acc[j] : 0.f;
-  }
-  *reinterpret_cast<uint4*>(at(din, n, iy, ix, c)) = pack8(acc);
+  if (db) fold_bias_partials(bsum, cc, db, red);
 }
 
-int upsample_bilinear_bwd(const Act& dout, const Act* relu_y, const Act& din, cudaStream_t st) {
-  if (din.C != dout.C || din.N != dout.N || din.C % 8) return DBX_ERR_ARG;
+int upsample_bilinear_bwd(const Act& dout, const Act* relu_y, const Act& din, cudaStream_t st, float* db) {
+  if (din.C != dout.C || din.N != dout.N || din.C % 8 || din.W > kUpMaxW) return DBX_ERR_ARG;
+  // an input pixel receives from at most ceil(2 * out / in) + 1 output pixels per axis
+  if (2 * ((dout.H + din.H - 1) / din.H) + 1 > kUpMaxTaps || 2 * ((dout.W + din.W - 1) / din.W) + 1 > kUpMaxTaps)
+    return DBX_ERR_ARG;
   const float sh = dout.H > 1 ? (float)(din.H - 1) / (float)(dout.H - 1) : 0.f;
   const float sw = dout.W > 1 ? (float)(din.W - 1) / (float)(dout.W - 1) : 0.f;
-  const size_t total = (size_t)din.N * din.H * din.W * (din.C / 8);
-  upsample_bwd_kernel<<<grid_for(total, 256), 256, 0, st>>>(dout, relu_y ? *relu_y : din, relu_y ? 1 : 0, din, sh, sw);
-  return (int)cudaGetLastError();
+  const int cc = din.C / 8;
+  const bool fold = db && (256 % cc) == 0;
+  upsample_bwd_kernel<<<din.N * din.H, 256, 0, st>>>(dout, relu_y ? *relu_y : din, relu_y ? 1 : 0, din, sh, sw,
+                                                         fold ? db : nullptr);
+  int rc = (int)cudaGetLastError();
+  if (!rc && db && !fold) rc = colsum(din, db, st);
+  return rc;
 }
 
 // ------------------------------------------------------------------------------------------------ bias gradient
-// db[c] += sum over pixels of dy[pixel][c].  blockDim = (C/8) * rows; thread (r, chunk) keeps 8 fp32 partials.
-__global__ void colsum_kernel(Act dy, float* __restrict__ db, int rows, size_t pixels, size_t pix_per_block) {
+// db[c] += sum over pixels of dy[pixel][c].  blockDim = (C/8) * rows; thread (r, chunk) keeps 8 fp32 partials over its
+// pixels (8 loads in flight), the block folds them through shared memory and issues ONE atomic per channel: the
+// atomics to the same few addresses serialise in L2, so their count (blocks x C) is what bounds the small layers —
+// a shuffle-only variant with one vector red per warp was 2.4x slower (session 3).
+__global__ void __launch_bounds__(256) colsum_kernel(Act dy, float* __restrict__ db, int rows, size_t pixels,
+                                                     size_t pix_per_block) {
   extern __shared__ float red[];  // [rows][C]
   const int cc = dy.C / 8;
   const int chunk = threadIdx.x % cc, r = threadIdx.x / cc;
@@ -250,12 +343,12 @@ __global__ void colsum_kernel(Act dy, float* __restrict__ db, int rows, size_t p
   for (int j = 0; j < 8; ++j) acc[j] = 0.f;
   const bf16* base = reinterpret_cast<const bf16*>(dy.ptr) + dy.coff + chunk * 8;
   size_t p = p0 + r;
-  for (; p + 3 * (size_t)rows < p1; p += 4 * (size_t)rows) {
-    uint4 u[4];
+  for (; p + 7 * (size_t)rows < p1; p += 8 * (size_t)rows) {
+    uint4 u[8];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) u[q] = ldg16(base + (p + q * (size_t)rows) * dy.cs);
+    for (int q = 0; q < 8; ++q) u[q] = ldg16(base + (p + q * (size_t)rows) * dy.cs);
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int q = 0; q < 8; ++q) {
       float f[8];
       unpack8(u[q], f);
 #pragma unroll
@@ -280,10 +373,12 @@ __global__ void colsum_kernel(Act dy, float* __restrict__ db, int rows, size_t p
 
 int colsum(const Act& dy, float* db, cudaStream_t st) {
   if (!db || dy.C % 8 || dy.C > 2048) return DBX_ERR_ARG;
+  { const char* e = getenv("DBX_NO_COLSUM"); if (e && e[0] == '1') return DBX_OK; }  // measurement only
   const int cc = dy.C / 8;
   int rows = 256 / cc; if (rows < 1) rows = 1;
   const size_t pixels = (size_t)dy.N * dy.H * dy.W;
-  int blocks = 8 * num_sms();
+  int blocks = 8 * num_sms();  // measured: fewer, fatter blocks are slower even on the 29 MB layers (latency-bound)
+  { const char* e = getenv("DBX_COLSUM_BLOCKS"); if (e && atoi(e) > 0) blocks = atoi(e) * num_sms(); }
   if ((size_t)blocks * rows > pixels) blocks = (int)((pixels + rows - 1) / rows);
   if (blocks < 1) blocks = 1;
   const size_t ppb = (pixels + blocks - 1) / blocks;

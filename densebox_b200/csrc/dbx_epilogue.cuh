@@ -33,6 +33,7 @@ struct EpiArgs {
   int tw, th, box_rows;                 // pixel box of one tile (rows = tw*th*tn <= 128)
   int out_W, out_H;                     // aux_mode 3: element index of the dropped activation
   const unsigned long long* rng; int rng_channels;
+  float* csum = nullptr;                // smem fp32 [cout]: running column sums of everything this CTA stored (or null)
 };
 
 __device__ __forceinline__ uint32_t bf162_as_u32(__nv_bfloat162 h) { return *reinterpret_cast<uint32_t*>(&h); }
@@ -245,6 +246,25 @@ __device__ __forceinline__ void epilogue_tma(const EpiArgs& e, const CUtensorMap
       if (leader) {
         tma_store_4d(tmO, sb, nt * e.block_n + j * 64, w0, h0, n0);
         bulk_commit();
+      }
+      if (e.csum) {
+        // Column sums of the finished box (bias gradient of the layer below).  Thread t: channel pair t & 31, rows
+        // 16 (t >> 5) .. + 15; a warp reads the 32 words of ONE 128-byte row per instruction (conflict-free under
+        // the swizzle).  Rows outside the image are exact zeros (zero-filled operands, no bias).  The box is not
+        // rewritten before every thread has passed the next sub-block's barrier.
+        const int t = (int)threadIdx.x - 64, cp = t & 31, r0 = (t >> 5) * 16;
+        float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int rr = r0 + i;
+          if (rr < e.box_rows) {
+            const uint32_t w = *reinterpret_cast<const uint32_t*>(
+                sb + (uint32_t)rr * 128u + (uint32_t)((((cp >> 2) ^ (rr & 7)) << 4) + ((cp & 3) << 2)));
+            s0 += bf16lo(w); s1 += bf16hi(w);
+          }
+        }
+        const int c = nt * e.block_n + j * 64 + 2 * cp;
+        if (2 * cp < ncols && c < e.cout) { atomicAdd(e.csum + c, s0); atomicAdd(e.csum + c + 1, s1); }
       }
     }
     tc_fence_before();

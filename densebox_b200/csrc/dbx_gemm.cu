@@ -123,7 +123,9 @@ struct FpropParams {
   int cin, cin_blocks;
   int m_tiles, n_tiles, block_n;
   int cout;
-  int stages;
+  float* colsum; int csum_off;  // fused bias gradient: global fp32 [cout], smem offset of the per-CTA partial sums
+  int debug;               // measurement only (DBX_DEBUG): 1 = no TMA loads, 2 = no MMAs — results are garbage
+  int stages, kps;         // pipeline stages; K blocks (64 channels of one tap) per stage
   uint32_t idesc, tmem_cols;
   const float* bias;
   int relu;
@@ -136,7 +138,11 @@ struct FpropParams {
   int tma_epi, nbuf, nbuf_log2, nsb;  // bf16 outputs: epilogue staged through `nbuf` (2/4/8) smem boxes, `nsb` 64-column blocks/tile
 };
 
-template <bool kCta2>
+// kMode: 1 / 2 / 4 = K blocks (one tap x 64 channels) per pipeline stage; 3 = column-box mode for 3x3 pad-1 layers:
+// 8 x 16 pixel tiles, ONE 8 x 18 input box per (filter column s, channel slice) serves the three filter rows (a row
+// shift = 8 pixels = one 1024-B swizzle atom, so the descriptor just starts r atoms further) and travels with its
+// three filter tiles behind one barrier: 12 MMAs per barrier round trip, A traffic 3 x 18 KB instead of 9 x 16 KB.
+template <bool kCta2, int kMode>
 __global__ void __launch_bounds__(kFpropThreads, 1)
 conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmX,
@@ -157,10 +163,14 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int ustep = cta2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const int m_units = cta2 ? (p.m_tiles + 1) >> 1 : p.m_tiles;        // odd tail: the extra tile is fully out of bounds
   const int total = m_units * p.n_tiles;
-  const uint32_t a_bytes = (uint32_t)(p.tw * p.th * p.tn) * 128u;
+  constexpr bool colbox = kMode == 3;
+  constexpr uint32_t kColBox = 18u * 8u * 128u;               // 8 x 18 pixels x 64 channels
+  const uint32_t a_bytes = colbox ? kColBox : (uint32_t)(p.tw * p.th * p.tn) * 128u;
   const uint32_t b_rows = cta2 ? (uint32_t)p.block_n >> 1 : (uint32_t)p.block_n;
   const uint32_t b_bytes = b_rows * 128u;
-  const uint32_t stage_bytes = 16384u + b_bytes;
+  const uint32_t slot_bytes = colbox ? kColBox + 3u * b_bytes : 16384u + b_bytes;  // one K block: A box + B box(es)
+  constexpr int kps = colbox ? 1 : kMode;                     // K blocks per stage (compile time: unrolled issue)
+  const uint32_t stage_bytes = (uint32_t)kps * slot_bytes;    // a stage holds kps K blocks behind ONE barrier
   const int num_kb = p.R * p.S * p.cin_blocks;
   // Unit order: output-channel tile fastest, so the CTAs running at the same time share the SAME pixel tile and the
   // activations stream from HBM once (the weights of all channel tiles stay L2-resident).  With the pixel tile
@@ -181,6 +191,8 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if constexpr (cta2) { tmem_alloc_2sm(&tmem_base_s, p.tmem_cols); tmem_relinquish_2sm(); }
     else { tmem_alloc(&tmem_base_s, p.tmem_cols); tmem_relinquish(); }
   }
+  float* csum = p.colsum ? reinterpret_cast<float*>(smem + p.csum_off) : nullptr;
+  if (csum) for (int c = threadIdx.x; c < p.cout; c += kFpropThreads) csum[c] = 0.f;
   tc_fence_before();
   if constexpr (cta2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
@@ -189,9 +201,17 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   // Shared-window addresses are computed once: the hot loops below must stay a few dozen instructions per K block,
   // a single warp issues them back to back (round 1 profile: the old MMA loop spent ~650 cycles/K-block on address
   // arithmetic and per-instruction election loops and was the bottleneck of EVERY layer).
-  const uint32_t smem_base = smem_u32(smem);
-  const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
-  const uint32_t tfull0 = smem_u32(&tfull_bar[0]), tempty0 = smem_u32(&tempty_bar[0]);
+  uint32_t smem_base = smem_u32(smem);
+  uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
+  uint32_t tfull0 = smem_u32(&tfull_bar[0]), tempty0 = smem_u32(&tempty_bar[0]);
+  // opaque to the optimiser: otherwise ptxas re-derives every window address inside the hot loops
+  // (S2R SR_CgaCtaId + LEA per barrier access, ~30 cycles of latency each on a single-warp issue loop)
+#ifndef DBX_OPAQUE
+#define DBX_OPAQUE 1
+#endif
+#if DBX_OPAQUE
+  asm volatile("" : "+r"(smem_base), "+r"(full0), "+r"(empty0), "+r"(tfull0), "+r"(tempty0));
+#endif
 
   if (warp == 0) {
     // ===================== TMA producer (whole warp walks the schedule, one elected lane issues) ===============
@@ -202,27 +222,74 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int h0 = ((mt / p.tiles_w) % p.tiles_h) * p.th - p.pad;
       const int n0 = (mt / (p.tiles_w * p.tiles_h)) * p.tn;
       const int brow = nt * p.block_n + (int)(rank * b_rows) * (cta2 ? 1 : 0);
-      int kcol = 0;
-      for (int r = 0; r < p.R; ++r)
-        for (int s = 0; s < p.S; ++s)
-          for (int cb = 0; cb < p.cin_blocks; ++cb, kcol += 64) {
+      if constexpr (colbox) {
+        for (int cb = 0; cb < p.cin_blocks; ++cb)
+          for (int sx = 0; sx < 3; ++sx) {
             mbar_wait_a(empty0 + 8u * stage, phase ^ 1);
             if (elect_one_sync()) {
-              const uint32_t sa = smem_base + (uint32_t)stage * stage_bytes, fb = full0 + 8u * stage;
-              if constexpr (cta2) {
-                // both CTAs' bytes land on the leader's barrier; only the leader arms it
-                if (rank == 0) mbar_arrive_expect_tx_a(fb, 2u * (a_bytes + b_bytes));
-                tma_load_4d_2sm_a(&tmA, fb, sa, cb * 64, w0 + s, h0 + r, n0);
-                tma_load_2d_2sm_a(&tmB, fb, sa + 16384u, kcol, brow);
+              const uint32_t fb = full0 + 8u * stage;
+              const uint32_t sa = smem_base + (uint32_t)stage * stage_bytes;
+              const int kc = sx * p.cin + cb * 64;              // filter column of tap (r = 0, s): + 3 * cin per row
+              if (p.debug & 1) {
+                if (rank == 0) mbar_arrive_expect_tx_a(fb, 0u);
+              } else if constexpr (cta2) {
+                if (rank == 0) mbar_arrive_expect_tx_a(fb, 2u * slot_bytes);
+                tma_load_4d_2sm_a(&tmA, fb, sa, cb * 64, w0 + sx, h0, n0);
+#pragma unroll
+                for (int r = 0; r < 3; ++r)
+                  tma_load_2d_2sm_a(&tmB, fb, sa + kColBox + (uint32_t)r * b_bytes, kc + r * 3 * p.cin, brow);
               } else {
-                mbar_arrive_expect_tx_a(fb, a_bytes + b_bytes);
-                tma_load_4d_a(&tmA, fb, sa, cb * 64, w0 + s, h0 + r, n0);
-                tma_load_2d_a(&tmB, fb, sa + 16384u, kcol, brow);
+                mbar_arrive_expect_tx_a(fb, slot_bytes);
+                tma_load_4d_a(&tmA, fb, sa, cb * 64, w0 + sx, h0, n0);
+#pragma unroll
+                for (int r = 0; r < 3; ++r)
+                  tma_load_2d_a(&tmB, fb, sa + kColBox + (uint32_t)r * b_bytes, kc + r * 3 * p.cin, brow);
               }
             }
             __syncwarp();
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
+        continue;
+      }
+      int kcol = 0, r = 0, sx = 0, cb = 0;
+      for (int kb0 = 0; kb0 < num_kb; kb0 += kps) {
+        int nk = num_kb - kb0; if (nk > kps) nk = kps;
+        mbar_wait_a(empty0 + 8u * stage, phase ^ 1);
+        if (elect_one_sync()) {
+          const uint32_t fb = full0 + 8u * stage;
+          uint32_t sa = smem_base + (uint32_t)stage * stage_bytes;
+          if (p.debug & 1) {
+            if (rank == 0) mbar_arrive_expect_tx_a(fb, 0u);
+            nk = 0;
+          } else if constexpr (cta2) {
+            // both CTAs' bytes land on the leader's barrier; only the leader arms it
+            if (rank == 0) mbar_arrive_expect_tx_a(fb, 2u * (uint32_t)nk * (a_bytes + b_bytes));
+          } else {
+            mbar_arrive_expect_tx_a(fb, (uint32_t)nk * (a_bytes + b_bytes));
+          }
+          int r2 = r, s2 = sx, cb2 = cb, kc2 = kcol;
+#pragma unroll
+          for (int j = 0; j < kps; ++j, sa += slot_bytes, kc2 += 64) {
+            if (j >= nk) break;
+            if constexpr (cta2) {
+              tma_load_4d_2sm_a(&tmA, fb, sa, cb2 * 64, w0 + s2, h0 + r2, n0);
+              tma_load_2d_2sm_a(&tmB, fb, sa + 16384u, kc2, brow);
+            } else {
+              tma_load_4d_a(&tmA, fb, sa, cb2 * 64, w0 + s2, h0 + r2, n0);
+              tma_load_2d_a(&tmB, fb, sa + 16384u, kc2, brow);
+            }
+            if (++cb2 == p.cin_blocks) { cb2 = 0; if (++s2 == p.S) { s2 = 0; ++r2; } }
+          }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < kps; ++j) {  // every lane tracks the (tap, channel slice) position: any lane may be elected
+          if (j >= nk) break;
+          kcol += 64;
+          if (++cb == p.cin_blocks) { cb = 0; if (++sx == p.S) { sx = 0; ++r; } }
+        }
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA; warp-uniform loop, one elected lane issues) ===============
@@ -234,16 +301,49 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         mbar_wait_a(tempty0 + 8u * buf, (use & 1) ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem + (uint32_t)(buf * p.block_n);
-        for (int kb = 0; kb < num_kb; ++kb) {
+        if constexpr (colbox) {
+          const int nst = 3 * p.cin_blocks;
+          for (int st = 0; st < nst; ++st) {
+            mbar_wait_a(full0 + 8u * stage, phase);
+            tc_fence_after();
+            if (elect_one_sync()) {
+              const uint32_t a_lo = (smem_base + (uint32_t)stage * stage_bytes) >> 4;
+              const uint64_t da0 = desc_hi | (uint64_t)a_lo, db0 = desc_hi | (uint64_t)(a_lo + (kColBox >> 4));
+              const uint32_t bt = b_bytes >> 4;
+              if (!(p.debug & 2)) {
+#pragma unroll
+                for (int r = 0; r < 3; ++r)
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) {  // filter row r: the box shifted by r image rows = r atoms (64 x 16 B)
+                    if constexpr (cta2)
+                      umma_bf16_2sm(d_tmem, da0 + 64 * r + 2 * k, db0 + (uint64_t)r * bt + 2 * k, p.idesc,
+                                    (uint32_t)((st | r | k) != 0));
+                    else
+                      umma_bf16(d_tmem, da0 + 64 * r + 2 * k, db0 + (uint64_t)r * bt + 2 * k, p.idesc,
+                                (uint32_t)((st | r | k) != 0));
+                  }
+              }
+              if constexpr (cta2) umma_commit_2sm_a(empty0 + 8u * stage, 3); else umma_commit_a(empty0 + 8u * stage);
+            }
+            __syncwarp();
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          }
+        } else
+        for (int kb0 = 0; kb0 < num_kb; kb0 += kps) {
+          int nk = num_kb - kb0; if (nk > kps) nk = kps;
           mbar_wait_a(full0 + 8u * stage, phase);
           tc_fence_after();
           if (elect_one_sync()) {
-            const uint32_t a_lo = (smem_base + (uint32_t)stage * stage_bytes) >> 4;
-            const uint64_t da = desc_hi | (uint64_t)a_lo, db = desc_hi | (uint64_t)(a_lo + 1024u);  // B at +16 KB
+            uint32_t a_lo = (smem_base + (uint32_t)stage * stage_bytes) >> 4;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {  // +32 B (2 x 16 B units) per UMMA_K = 16
-              if constexpr (cta2) umma_bf16_2sm(d_tmem, da + 2 * k, db + 2 * k, p.idesc, (uint32_t)((kb | k) != 0));
-              else umma_bf16(d_tmem, da + 2 * k, db + 2 * k, p.idesc, (uint32_t)((kb | k) != 0));
+            for (int j = 0; j < kps; ++j, a_lo += slot_bytes >> 4) {
+              if (j >= nk || (p.debug & 2)) break;
+              const uint64_t da = desc_hi | (uint64_t)a_lo, db = desc_hi | (uint64_t)(a_lo + 1024u);  // B at +16 KB
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {  // +32 B (2 x 16 B units) per UMMA_K = 16
+                if constexpr (cta2) umma_bf16_2sm(d_tmem, da + 2 * k, db + 2 * k, p.idesc, (uint32_t)((kb0 | j | k) != 0));
+                else umma_bf16(d_tmem, da + 2 * k, db + 2 * k, p.idesc, (uint32_t)((kb0 | j | k) != 0));
+              }
             }
             if constexpr (cta2) umma_commit_2sm_a(empty0 + 8u * stage, 3); else umma_commit_a(empty0 + 8u * stage);
           }
@@ -265,6 +365,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       ea.block_n = p.block_n; ea.nsb = p.nsb; ea.nbuf_log2 = p.nbuf_log2;
       ea.tw = p.tw; ea.th = p.th; ea.box_rows = p.tw * p.th * p.tn;
       ea.out_W = p.out_W; ea.out_H = p.out_H; ea.rng = p.rng; ea.rng_channels = p.rng_channels;
+      ea.csum = csum;
       const int my_tiles = u0 < total ? (total - 1 - u0) / ustep + 1 : 0;
       auto tile_of = [&](int it, int& nt, int& w0, int& h0, int& n0) {
         DBX_UNIT_TILE(u0 + it * ustep, nt_, mt_);
@@ -349,6 +450,8 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   tc_fence_before();
   __syncwarp();
   if constexpr (cta2) cluster_sync_all(); else __syncthreads();
+  if (csum)  // one global atomic per channel and CTA
+    for (int c = threadIdx.x; c < p.cout; c += kFpropThreads) { const float v = csum[c]; if (v != 0.f) atomicAdd(p.colsum + c, v); }
   if (warp == 1) {
     tc_fence_after();
     if constexpr (cta2) tmem_dealloc_2sm(tmem, p.tmem_cols); else tmem_dealloc(tmem, p.tmem_cols);
@@ -371,7 +474,7 @@ int conv_fprop(const Act& x, const void* wk, int R, int S, int pad, const Act& o
   if ((epi.aux_mode == 1 || epi.aux_mode == 2) && (!epi.aux || epi.aux_cs % 8 || epi.aux_coff % 8)) return DBX_ERR_ARG;
   if (epi.aux_mode == 3 && (!epi.rng || epi.rng_channels % 128)) return DBX_ERR_ARG;
   if (R == 3 && S == 3 && pad == 1 && x.C == 64 && out.C == 64 && !epi.out_fp32 && block_n <= 0 &&
-      epi.aux_mode != 3) {
+      (epi.aux_mode == 1 || epi.aux_mode == 2)) {  // masked epilogue (conv1_2 dgrad); without a mask colbox + CTA pairs wins
     const char* e = getenv("DBX_HALO");
     if (!(e && e[0] == '0')) {  // 64->64 3x3 layers (conv1_2 fwd/dgrad): column-box kernel, resident filter (A/B: DBX_HALO=0)
       const int rc = conv3x3_halo(x, wk, out, epi, stream);
@@ -384,14 +487,34 @@ int conv_fprop(const Act& x, const void* wk, int R, int S, int pad, const Act& o
   Tile t = choose_tile(out.W, out.H, out.N, false);
   int tma_epi = epi.out_fp32 ? 0 : 1;
   { const char* e = getenv("DBX_DIRECT_EPI"); if (e && e[0] == '1' && epi.aux_mode != 3) tma_epi = 0; }  // A/B switch
+  // Column-box mode (see the kernel) for the 3x3 pad-1 layers on maps that 8 x 16 tiles cover without much waste.
+  // Measured (tools/bench_colbox.py, B = 32, generic -> colbox + CTA pairs, TFLOP/s): conv2_1 dgrad 557 -> 1004,
+  // conv2_2 975 -> 1322, conv3_1 dgrad 811 -> 1129, conv4_2 1161 -> 1281, conv3_2 1209 -> 1229: the generic mode is
+  // bound by barrier round trips (one per 4 MMAs) and TMA delivery on the narrow layers.
+  int colbox = 0;
+  int colbox_max_n = 256;
+  { const char* e = getenv("DBX_COLBOX_MAX_N"); if (e) colbox_max_n = atoi(e); }
+  if (R == 3 && S == 3 && pad == 1 && tma_epi && block_n <= colbox_max_n && block_n % 32 == 0 && epi.aux_mode != 3) {
+    const double cover = (double)out.W * out.H / ((double)((out.W + 7) / 8 * 8) * ((out.H + 15) / 16 * 16));
+    colbox = cover >= 0.87 ? 1 : 0;   // 60 x 60 and 30 x 30 maps: 0.879 (measured: still +30 % on conv3_1 dgrad)
+  }
+  { const char* e = getenv("DBX_COLBOX_FPROP"); if (e && R == 3 && S == 3 && pad == 1 && tma_epi) colbox = atoi(e) != 0; }
+  if (colbox) {
+    t.tw = 8; t.th = 16; t.tn = 1;
+    t.tiles_w = (out.W + 7) / 8; t.tiles_h = (out.H + 15) / 16; t.tiles_n = out.N;
+  }
   // CTA pairs (tcgen05.mma.cta_group::2) whenever the B tile is worth halving
   // (measured round 1: +4..6 % on the N = 256 layers once the MMA issue loop was lean; before that the kernel was
   // issue-bound and pairing changed nothing.  ConvEpilogue::force_cta2 = 0 or DBX_CTA2=0 switches it off.)
-  const bool cta2_ok = tma_epi && block_n >= 256 && t.count() >= 2 && num_sms() >= 2;
+  int cta2_min_n = colbox ? 64 : 256;
+  { const char* e = getenv("DBX_CTA2_MIN_N"); if (e) cta2_min_n = atoi(e); }
+  const bool cta2_ok = tma_epi && block_n >= cta2_min_n && block_n % 32 == 0 && t.count() >= 2 && num_sms() >= 2;
   int cta2 = (cta2_ok && epi.force_cta2 != 0) ? 1 : 0;
   { const char* e = getenv("DBX_CTA2"); if (e && cta2_ok) cta2 = e[0] == '1'; }  // A/B switch for measurements
   CUtensorMap tmA, tmB, tmO, tmX;
-  int rc = encode_act_map(&tmA, x, t);
+  Tile ta = t;
+  if (colbox) ta.th = 18;
+  int rc = encode_act_map(&tmA, x, ta);
   if (rc) return rc;
   rc = encode_mat_map(&tmB, wk, out.C, R * S * x.C, cta2 ? block_n / 2 : block_n);
   if (rc) return rc;
@@ -419,28 +542,64 @@ int conv_fprop(const Act& x, const void* wk, int R, int S, int pad, const Act& o
   p.m_tiles = t.count(); p.n_tiles = (out.C + block_n - 1) / block_n; p.block_n = block_n;
   p.cout = out.C;
   p.cta2 = cta2;
-  const int stage_bytes = 16384 + (cta2 ? block_n / 2 : block_n) * 128;
+  const int slot_bytes = colbox ? 18432 + 3 * (cta2 ? block_n / 2 : block_n) * 128
+                                : 16384 + (cta2 ? block_n / 2 : block_n) * 128;
+  // K blocks per stage: a barrier round trip of the single-warp issue loops costs ~250 ns (tools/bench_debug.py:
+  // conv2_2 with neither TMA nor MMA still takes 0.113 ms of 0.152), which a 64-wide tile (128 cycles of MMA per K
+  // block) cannot hide -> batch K blocks behind one barrier
+  const int b_rows_cta = cta2 ? block_n / 2 : block_n;
+  p.kps = b_rows_cta <= 64 ? 2 : 1;  // measured (tools/bench_kps.py): wider tiles lose more to the coarser pipeline
+  { const char* e = getenv("DBX_KPS"); if (e && atoi(e) >= 1 && atoi(e) <= 4) p.kps = atoi(e); }
+  if (p.kps > R * S * (x.C / 64)) p.kps = R * S * (x.C / 64);
+  if (colbox) p.kps = 1;
   p.tma_epi = tma_epi;
   p.nsb = (block_n + 63) / 64;
   p.nbuf = 4;
-  if (tma_epi && (kSmemBudget - 4 * kEpiBuf) / stage_bytes < 4) p.nbuf = 2;  // keep >= 4 operand stages
+  if (tma_epi && (kSmemBudget - 4 * kEpiBuf) / slot_bytes < 4) p.nbuf = 2;  // keep >= 4 operand K blocks in flight
+  if (colbox) p.nbuf = (block_n <= 64 && x.C <= 64) ? 4 : 2;  // measured (tools/bench_colbox.py)
   if (tma_epi && (epi.epi_bufs == 2 || epi.epi_bufs == 4 || epi.epi_bufs == 8)) p.nbuf = epi.epi_bufs;
+  { const char* e = getenv("DBX_EPI_BUFS"); if (e && tma_epi && (atoi(e) == 2 || atoi(e) == 4 || atoi(e) == 8)) p.nbuf = atoi(e); }
   p.nbuf_log2 = p.nbuf == 8 ? 3 : (p.nbuf == 4 ? 2 : 1);
   const int ring = tma_epi ? p.nbuf * kEpiBuf : 0;
+  while (p.kps > 1 && (kSmemBudget - ring) / (p.kps * slot_bytes) < 2) p.kps >>= 1;
+  if (p.kps == 3) p.kps = 2;
+  const int stage_bytes = p.kps * slot_bytes;
   p.stages = (kSmemBudget - ring) / stage_bytes;
   if (p.stages > kMaxStages) p.stages = kMaxStages;
+  { const char* e = getenv("DBX_STAGES"); if (e && atoi(e) >= 2 && atoi(e) < p.stages) p.stages = atoi(e); }
   if (p.stages < 2) return DBX_ERR_ARG;
+  // fused column sums (bias gradient of the layer below): need cout floats of spare shared memory behind the ring
+  bool colsum_after = false;
+  p.colsum = nullptr; p.csum_off = 0;
+  if (epi.colsum) {
+    if (epi.bias) return DBX_ERR_ARG;
+    const int used = p.stages * stage_bytes + ring;
+    const char* e = getenv("DBX_FUSED_COLSUM");
+    if (tma_epi && used + out.C * 4 <= kSmemBudget && !(e && e[0] == '0')) { p.colsum = epi.colsum; p.csum_off = used; }
+    else colsum_after = true;   // no room (or fp32 output): same result from the stand-alone kernel after the launch
+  }
   p.idesc = umma_idesc_bf16(cta2 ? 256 : 128, block_n, 0, 0);
   p.tmem_cols = tmem_cols_for(2 * block_n);
+  { const char* e = getenv("DBX_DEBUG"); p.debug = e ? atoi(e) : 0; }
   p.bias = epi.bias; p.relu = epi.relu;
   p.aux = (const bf16*)epi.aux; p.aux_cs = epi.aux_cs; p.aux_coff = epi.aux_coff; p.aux_mode = epi.aux_mode;
   p.out = out.ptr; p.out_cs = out.cs; p.out_coff = out.coff; p.out_fp32 = epi.out_fp32;
   p.rng = epi.rng; p.rng_channels = epi.rng_channels;
 
-  static int attr_rc1 = set_max_smem((const void*)conv_fprop_kernel<false>);
-  static int attr_rc2 = set_max_smem((const void*)conv_fprop_kernel<true>);
-  if (attr_rc1 || attr_rc2) return attr_rc1 ? attr_rc1 : attr_rc2;
-  const size_t smem = (size_t)p.stages * stage_bytes + ring + 1024;
+  if (p.kps == 3) p.kps = 2;
+  typedef void (*FpropFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const FpropParams);
+  static const FpropFn fns[2][4] = {
+      {conv_fprop_kernel<false, 1>, conv_fprop_kernel<false, 2>, conv_fprop_kernel<false, 4>, conv_fprop_kernel<false, 3>},
+      {conv_fprop_kernel<true, 1>, conv_fprop_kernel<true, 2>, conv_fprop_kernel<true, 4>, conv_fprop_kernel<true, 3>}};
+  static int attr_rc = [] {
+    int rc = 0;
+    for (int a = 0; a < 2; ++a)
+      for (int b = 0; b < 4; ++b) { const int r = set_max_smem((const void*)fns[a][b]); if (r) rc = r; }
+    return rc;
+  }();
+  if (attr_rc) return attr_rc;
+  const FpropFn fn = fns[cta2 ? 1 : 0][colbox ? 3 : (p.kps == 4 ? 2 : (p.kps == 2 ? 1 : 0))];
+  const size_t smem = (size_t)p.stages * stage_bytes + ring + (p.colsum ? (size_t)out.C * 4 : 0) + 1024;
   cudaLaunchConfig_t cfg{};
   cfg.blockDim = dim3(kFpropThreads);
   cfg.dynamicSmemBytes = smem;
@@ -459,8 +618,9 @@ int conv_fprop(const Act& x, const void* wk, int R, int S, int pad, const Act& o
   attr[0].val.clusterDim.x = cta2 ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
   cfg.gridDim = dim3(grid);
-  if (cta2) return (int)cudaLaunchKernelEx(&cfg, conv_fprop_kernel<true>, tmA, tmB, tmO, tmX, p);
-  return (int)cudaLaunchKernelEx(&cfg, conv_fprop_kernel<false>, tmA, tmB, tmO, tmX, p);
+  rc = (int)cudaLaunchKernelEx(&cfg, fn, tmA, tmB, tmO, tmX, p);
+  if (rc == 0 && colsum_after) rc = colsum(out, epi.colsum, stream);
+  return rc;
 }
 
 // ------------------------------------------------------------------------------------------------ wgrad kernel
