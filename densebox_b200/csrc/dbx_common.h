@@ -82,6 +82,9 @@ int maxpool2x2_bwd(const Act& y, const Act& dp, const Act* add, const Act& dy, c
 int upsample_bilinear_fwd(const Act& in, const Act& out, cudaStream_t st);
 int upsample_bilinear_bwd(const Act& dout, const Act* relu_y, const Act& din, cudaStream_t st, float* db = nullptr);
 int colsum(const Act& dy, float* db, cudaStream_t st);
+// data gradient of the block-diagonal conv5_2 heads + dropout backward (+ optional bias gradient of conv5_1 in db)
+int heads2_dgrad(const void* d_head, const void* wd, void* out, size_t pixels, int K, int nh, const int* ch_start,
+                 int drop_mode, const void* mask, const unsigned long long* rng, float* db, cudaStream_t st);
 int pack_weights(const float* src, int co, int ci, int R, int S, long s_co, long s_ci, long s_r, long s_s, void* dstK,
                  long ldK, long rowK, long kK, int cin_pad, void* dstD, long ldD, long rowD, long kD, int cout_pad,
                  float* dstF, cudaStream_t st);

@@ -386,6 +386,127 @@ int colsum(const Act& dy, float* db, cudaStream_t st) {
   return (int)cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------------ heads: dgrad of conv5_2
+// d_hd[pix][i] = drop(pix, i) * sum_c d_head[pix][c] * W2[c][i]  (DenseBox.py:149-178 backward: conv5_2_* then
+// Dropout).  W2 is block-diagonal (head h owns rows ch_start[h] .. ch_start[h+1]-1 and columns 512h .. 512h+511), so a
+// column needs at most 8 products: this is a 236 MB store, not a GEMM — as a K = 64 tensor-core launch it was bound
+// by its epilogue (0.115 ms); here a thread owns 16 channels (one 32-byte sector per store pair), streams pixels, and
+// also folds the bias gradient of conv5_1 (column sums of what it stores) so d_hd is not read back for it.
+struct Heads2DgradParams {
+  const bf16* d_head;      // [pixels][64] bf16 (channels >= HC are zero)
+  const bf16* wd;          // [K][64] bf16: wd[i][c] = W2[c][i]
+  bf16* out;               // [pixels][K]
+  const bf16* mask;        // drop_mode 2: [pixels][K] {0,2}
+  const unsigned long long* rng;  // drop_mode 3: {seed, offset}
+  float* db;               // [K] or null
+  int K, nh, drop_mode;
+  int ch_start[5];
+  size_t pixels;
+};
+
+__global__ void __launch_bounds__(256) heads2_dgrad_kernel(const Heads2DgradParams p) {
+  extern __shared__ float ws[];  // [8][K]: ws[c][i] = W2[ch_start[head(i)] + c][i] (0 beyond the head's rows)
+  __shared__ float red[256 * 8];
+  const int K = p.K;
+  for (int e = threadIdx.x; e < 8 * K; e += blockDim.x) {
+    const int c = e / K, i = e - c * K, h = i >> 9;
+    int c0 = 0, nc = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) if (h == k) { c0 = p.ch_start[k]; nc = p.ch_start[k + 1] - c0; }
+    ws[e] = c < nc ? __bfloat162float(p.wd[(size_t)i * 64 + c0 + c]) : 0.f;
+  }
+  __syncthreads();
+  const int tpp = K / 16;                       // threads per pixel
+  const int ppb = (int)blockDim.x / tpp;        // pixel slots per block
+  const int slot = (int)threadIdx.x / tpp, i0 = ((int)threadIdx.x - slot * tpp) * 16;
+  const int h = i0 >> 9;
+  int c0 = 0, nc = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) if (h == k) { c0 = p.ch_start[k]; nc = p.ch_start[k + 1] - c0; }
+  unsigned long long seed = 0, off = 0;
+  if (p.drop_mode == 3) { seed = p.rng[0]; off = p.rng[1]; }
+  float bsum[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) bsum[j] = 0.f;
+  if (slot < ppb)
+  for (size_t pix = (size_t)blockIdx.x * ppb + slot; pix < p.pixels; pix += (size_t)gridDim.x * ppb) {
+    float acc[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+    const bf16* g = p.d_head + pix * 64 + c0;
+    for (int c = 0; c < nc; ++c) {
+      const float gv = __bfloat162float(g[c]);
+      const float4* w4 = reinterpret_cast<const float4*>(ws + (size_t)c * K + i0);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 w = w4[q];
+        acc[4 * q] += gv * w.x; acc[4 * q + 1] += gv * w.y; acc[4 * q + 2] += gv * w.z; acc[4 * q + 3] += gv * w.w;
+      }
+    }
+    if (p.drop_mode == 3) {
+      const uint32_t bits = dropout_bits16(pix * (unsigned long long)K + (unsigned long long)i0, seed, off);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) acc[j] = ((bits >> j) & 1u) ? 2.f * acc[j] : 0.f;
+    } else if (p.drop_mode == 2) {
+      float m[16];
+      unpack8(ldg16(p.mask + pix * K + i0), m);
+      unpack8(ldg16(p.mask + pix * K + i0 + 8), m + 8);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) acc[j] *= m[j];
+    }
+    const uint4 q0 = pack8(acc), q1 = pack8(acc + 8);
+    uint4* o = reinterpret_cast<uint4*>(p.out + pix * K + i0);
+    o[0] = q0; o[1] = q1;
+    if (p.db) {
+      float f[16];
+      unpack8(q0, f); unpack8(q1, f + 8);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) bsum[j] += f[j];
+    }
+  }
+  if (p.db) {  // fold the pixel slots of the block, then one atomic per channel
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      __syncthreads();
+#pragma unroll
+      for (int j = 0; j < 8; ++j) red[threadIdx.x * 8 + j] = bsum[half * 8 + j];
+      __syncthreads();
+      if (slot == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float sum = 0.f;
+          for (int k = 0; k < ppb; ++k) sum += red[((size_t)k * tpp + threadIdx.x) * 8 + j];
+          if (sum != 0.f) atomicAdd(p.db + i0 + half * 8 + j, sum);
+        }
+      }
+    }
+  }
+}
+
+int heads2_dgrad(const void* d_head, const void* wd, void* out, size_t pixels, int K, int nh, const int* ch_start,
+                 int drop_mode, const void* mask, const unsigned long long* rng, float* db, cudaStream_t st) {
+  if (!d_head || !wd || !out || !ch_start || nh < 1 || nh > 4 || K != 512 * nh) return DBX_ERR_ARG;
+  if ((drop_mode == 2 && !mask) || (drop_mode == 3 && !rng) || drop_mode == 1 || drop_mode < 0 || drop_mode > 3)
+    return DBX_ERR_ARG;
+  Heads2DgradParams p{};
+  p.d_head = (const bf16*)d_head; p.wd = (const bf16*)wd; p.out = (bf16*)out; p.mask = (const bf16*)mask;
+  p.rng = rng; p.db = db; p.K = K; p.nh = nh; p.drop_mode = drop_mode; p.pixels = pixels;
+  for (int i = 0; i < 5; ++i) p.ch_start[i] = ch_start[i];
+  for (int h = 0; h < nh; ++h) if (ch_start[h + 1] - ch_start[h] > 8 || ch_start[h + 1] > 64) return DBX_ERR_ARG;
+  const int tpp = K / 16;
+  const int threads = tpp * (256 / tpp > 0 ? 256 / tpp : 1);
+  if (threads > 256) return DBX_ERR_ARG;
+  const size_t smem = (size_t)8 * K * sizeof(float);
+  static int attr_rc = (int)cudaFuncSetAttribute((const void*)heads2_dgrad_kernel,
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2048 * 4);
+  if (attr_rc) return attr_rc;
+  const int ppb = threads / tpp;
+  int blocks = 4 * num_sms();
+  if ((size_t)blocks * ppb > pixels) blocks = (int)((pixels + ppb - 1) / ppb);
+  heads2_dgrad_kernel<<<blocks, threads, smem, st>>>(p);
+  return (int)cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------------------ weights
 // Generic strided fp32 [co,ci,R,S] -> bf16 K-major  dstK[(rowK+o)*ldK + kK + (r*S+s)*cin_pad + i]
 //                                 and bf16 dgrad    dstD[(rowD+i)*ldD + kD + ((R-1-r)*S+(S-1-s))*cout_pad + o]

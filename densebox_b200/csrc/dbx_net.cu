@@ -450,6 +450,7 @@ struct Net {
     Act d_p2 = act("d_p2", h4, w4, 128), d_a22 = act("d_a22", h2, w2, 128), d_a21 = act("d_a21", h2, w2, 128);
     Act d_p1 = act("d_p1", h2, w2, 64), d_a12 = act("d_a12", H, W, 64), d_a11 = act("d_a11", H, W, 64);
 
+    bool heads1_bias_done = false;
     if (stage != 1) {
     if (variant >= 1) {
       Act rp = act("rp", h8, w8, 64), r1 = act("r1", h8 - 2, w8 - 2, 64);
@@ -472,13 +473,26 @@ struct Net {
       const Group& g = groups[group_id("heads2")];
       if (side && !profiling) { ++launches; DBX_TRY(blockdiag_mask(G32() + g.w_off, g.rows, g.ld, nh, ch_start, side)); }
       else DBX_K("blockdiag_mask", 0.0, blockdiag_mask(G32() + g.w_off, g.rows, g.ld, nh, ch_start, st));
-      ConvEpilogue e;
-      if (drop_mode == 2) { e.aux = buf("drop"); e.aux_cs = 512 * nh; e.aux_mode = 2; e.epi_bufs = 8; }
-      else if (drop_mode == 3) { e.aux_mode = 3; e.rng = (const unsigned long long*)buf("rng"); e.rng_channels = 512 * nh; }
-      DBX_K("dgrad:heads2", 2.0 * pixels(d_head64) * macs_of("heads2"),
-            conv_fprop(d_head64, wd_of("heads2"), 1, 1, 0, d_hd, e, 0, st));
+      // DBX_HEADS2_DGRAD=1: streaming kernel (heads2_dgrad) instead of the K = 64 tensor-core launch.  Kept as an
+      // independent implementation for parity (tests/test_gpu_fused_bias.py); measured 0.18 ms against 0.115 ms —
+      // Philox + dropout + bias fold per element make it instruction-bound — so it is not the default.
+      bool direct = false;
+      { const char* e = getenv("DBX_HEADS2_DGRAD"); if (e && e[0] == '1') direct = true; }
+      if (direct) {
+        heads1_bias_done = fuse;
+        DBX_K("dgrad:heads2", 2.0 * pixels(d_head64) * macs_of("heads2"),
+              heads2_dgrad(d_head64.ptr, wd_of("heads2"), d_hd.ptr, (size_t)N * h4 * w4, 512 * nh, nh, ch_start,
+                           drop_mode, buf("drop"), (const unsigned long long*)buf("rng"),
+                           fuse ? gb_of("heads1") : nullptr, st));
+      } else {
+        ConvEpilogue e;
+        if (drop_mode == 2) { e.aux = buf("drop"); e.aux_cs = 512 * nh; e.aux_mode = 2; e.epi_bufs = 8; }
+        else if (drop_mode == 3) { e.aux_mode = 3; e.rng = (const unsigned long long*)buf("rng"); e.rng_channels = 512 * nh; }
+        DBX_K("dgrad:heads2", 2.0 * pixels(d_head64) * macs_of("heads2"),
+              conv_fprop(d_head64, wd_of("heads2"), 1, 1, 0, d_hd, e, 0, st));
+      }
     }
-    DBX_TRY(wgrad(fus, d_hd, "heads1", 1, 0, st));
+    DBX_TRY(wgrad(fus, d_hd, "heads1", 1, 0, st, heads1_bias_done));
     DBX_TRY(dgrad(d_hd, "heads1", 1, 0, d_fus, nullptr, st));
     // conv4 block
     DBX_K("upsample_bwd", 0.0, upsample_bilinear_bwd(d_fus_up, &a44, d_a44, st, fuse ? gb_of("conv4_4") : nullptr));
