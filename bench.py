@@ -36,8 +36,19 @@ def peaks():
     return {"hbm_gbs": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
 
 
+def traffic_from_profile(variant, B):
+    """DRAM bytes per launch of the dominant kernel family from the committed `ncu --set full` capture
+    (profiles/ncu_traffic_r1.json: dram__bytes_read.sum + dram__bytes_write.sum averaged over the 25 fprop/dgrad
+    launches of one B=32 DenseBox step); null for any other workload."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic_r1.json")
+    if variant != "densebox" or B != 32 or not os.path.exists(p):
+        return None
+    d = json.load(open(p))
+    return {"value": d["dram_mb_per_launch"], "unit": "MB per launch", "launches": d["launches"], "source": d["source"]}
+
+
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms while the timed region runs."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -48,7 +59,7 @@ class ClockSampler:
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -281,7 +292,8 @@ def main():
         roof = {"kernel": "conv_fprop_kernel + conv3x3_halo_kernel (tcgen05 implicit GEMM: %d fprop + %d dgrad launches per step)"
                           % (conv[0][2], conv[1][2]),
                 "bound": "tensor", "achieved": round(ach, 1), "peak": pk["tf_sustained"], "unit": "TFLOP/s",
-                "frac": round(ach / pk["tf_sustained"], 4), "traffic": None, "peak_source": pk["source"],
+                "frac": round(ach / pk["tf_sustained"], 4), "traffic": traffic_from_profile(variant, B),
+                "peak_source": pk["source"],
                 "algorithmic_gflop_per_launch_avg": round(fl / max(conv[0][2] + conv[1][2], 1) * 1e-9, 2),
                 "avg_launch_ms": round(tm / max(conv[0][2] + conv[1][2], 1), 4),
                 "step_tflops": round(GFLOP_TRAIN[variant] * B / ms, 1),

@@ -11,13 +11,13 @@ from tools.bench_layers import timeit
 B = 32
 SHAPES = [("conv1_2", 240, 64, 64), ("conv2_1 fprop", 120, 64, 128), ("conv2_1 dgrad", 120, 128, 64),
           ("conv2_2", 120, 128, 128), ("conv3_1 dgrad", 60, 256, 128), ("conv3_1 fprop", 60, 128, 256),
-          ("conv3_2", 60, 256, 256), ("conv4_1 fprop", 30, 256, 512), ("conv4_1 dgrad", 30, 512, 256),
-          ("conv4_2", 30, 512, 512)]
+          ("conv3_2", 60, 256, 256), ("conv4_2", 30, 512, 512)]
 CFG = [  # label, env
-    ("generic", {"DBX_COLBOX_FPROP": "0", "DBX_KPS": "1", "DBX_HALO": "1"}),
     ("default", {}),
-    ("colbox cta2 nbuf4", {"DBX_COLBOX_FPROP": "1", "DBX_EPI_BUFS": "4", "DBX_HALO": "0"}),
-    ("colbox cta2 nbuf2", {"DBX_COLBOX_FPROP": "1", "DBX_EPI_BUFS": "2", "DBX_HALO": "0"}),
+    ("colbox nbuf2", {"DBX_COLBOX_FPROP": "1", "DBX_EPI_BUFS": "2", "DBX_HALO": "0"}),
+    ("colbox nbuf4", {"DBX_COLBOX_FPROP": "1", "DBX_EPI_BUFS": "4", "DBX_HALO": "0"}),
+    ("colbox nbuf8", {"DBX_COLBOX_FPROP": "1", "DBX_EPI_BUFS": "8", "DBX_HALO": "0"}),
+    ("halo", {"DBX_COLBOX_FPROP": "0", "DBX_HALO": "1"}),
 ]
 KEYS = sorted({k for _, e in CFG for k in e})
 g = torch.Generator(device="cuda").manual_seed(0)

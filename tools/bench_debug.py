@@ -10,8 +10,9 @@ from densebox_b200 import ops
 from tools.bench_layers import timeit
 
 B = 32
-SHAPES = [("conv2_2", 120, 128, 128, 3), ("conv2_1 dgrad", 120, 128, 64, 3), ("conv2_1 fprop", 120, 64, 128, 3),
-          ("conv3_2", 60, 256, 256, 3), ("conv4_2", 30, 512, 512, 3), ("heads2 dgrad", 60, 64, 1024, 1)]
+SHAPES = [("conv1_2", 240, 64, 64, 3), ("conv2_2", 120, 128, 128, 3), ("conv2_1 dgrad", 120, 128, 64, 3),
+          ("conv2_1 fprop", 120, 64, 128, 3), ("conv3_2", 60, 256, 256, 3), ("conv4_2", 30, 512, 512, 3),
+          ("heads1", 60, 768, 1024, 1), ("heads2 dgrad", 60, 64, 1024, 1)]
 g = torch.Generator(device="cuda").manual_seed(0)
 a = torch.randn(8192, 8192, device="cuda", dtype=torch.bfloat16)
 for _ in range(200):
@@ -23,8 +24,7 @@ for name, H, cin, cout, R in SHAPES:
     out = torch.empty(B, H, H, cout, dtype=torch.bfloat16, device="cuda")
     bias = torch.zeros(cout, device="cuda")
     flops = 2.0 * B * H * H * cin * cout * R * R
-    for kps in sys.argv[1:] or ["1", "2"]:
-        os.environ["DBX_KPS"] = kps
+    for kps in ["-"]:
         for dbg in ("0", "1", "2", "3"):
             os.environ["DBX_DEBUG"] = dbg
             t = timeit(lambda: ops.conv_fprop(x, wk, R, R, R // 2, out, bias=bias, relu=True), n=30)
