@@ -705,12 +705,13 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
             tma_load_4d_2sm_a(&tmDy, fb, sa, m * 128, w0, h0, n0);
             tma_load_4d_2sm_a(&tmDy, fb, sa + box_bytes, m * 128 + 64, w0, h0, n0);
           } else if (p.colbox) {
-            // q0 = filter column s: dY tile(s) + ONE input box shifted by s-1 columns, one row of halo above/below
+            // dY tile(s) + ONE input box shifted by s-1 columns, one row of halo above/below
             const bool two = m * 128 + 64 < p.cout;
             mbar_arrive_expect_tx_a(fb, (two ? 2u : 1u) * box_bytes + 18432u);
             tma_load_4d_a(&tmDy, fb, sa, m * 128, w0, h0, n0);
             if (two) tma_load_4d_a(&tmDy, fb, sa + box_bytes, m * 128 + 64, w0, h0, n0);
-            tma_load_4d_a(&tmX, fb, sa + 2u * box_bytes, 0, w0 + q0 - 1, h0 - 1, n0);
+            // q0 = (channel slice, filter column): slice q0 / 3, column q0 % 3
+            tma_load_4d_a(&tmX, fb, sa + 2u * box_bytes, (q0 / 3) * 64, w0 + q0 % 3 - 1, h0 - 1, n0);
           } else {
             mbar_arrive_expect_tx_a(fb, box_bytes * (2u + (uint32_t)nvalid));
             tma_load_4d_a(&tmDy, fb, sa, m * 128, w0, h0, n0);
@@ -784,8 +785,9 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
         uint32_t v[16];
         tmem_ld_x16(taddr + c0, v);
         tmem_ld_wait();
-        // colbox: column block c0/64 is filter row r, q0 is filter column s -> tap r*3+s of dw[co][tap][ci]
-        float* dst = p.colbox ? drow + ((c0 >> 6) * 3 + q0) * 64 + (c0 & 63) : drow + c0;
+        // colbox: column block c0/64 is filter row r, q0 = 3 * slice + s -> tap r*3+s, channels 64*slice.. of dw[co][tap][ci]
+        float* dst = p.colbox ? drow + ((c0 >> 6) * 3 + q0 % 3) * (p.cin_blocks * 64) + (q0 / 3) * 64 + (c0 & 63)
+                              : drow + c0;
         if (valid && (p.colbox || (q0 + c0 / 64) < p.q_total)) {
 #pragma unroll
           for (int j = 0; j < 4; ++j)
@@ -822,9 +824,13 @@ int conv_wgrad(const Act& x, const Act& dy, int R, int S, int pad, float* dw, in
   if (block_n % 64 || block_n > 256 || block_n < 64) return DBX_ERR_ARG;
 
   Tile t = choose_tile(dy.W, dy.H, dy.N, true);
-  // Cin = 64 3x3 layers (conv1_2, conv2_1): column-box variant, see WgradParams::colbox
-  int colbox = (R == 3 && S == 3 && pad == 1 && x.C == 64 && block_n_in <= 0) ? 1 : 0;
-  { const char* e = getenv("DBX_COLBOX"); if (e && e[0] == '0') colbox = 0; }
+  // 3x3 layers with Cin <= 128 (conv1_2, conv2_1, conv2_2, conv3_1): column-box variant, see WgradParams::colbox.
+  // Measured (tools/bench_wgrad.py, TFLOP/s, generic -> column box): conv2_2 932 -> 1294, conv3_1 876 -> 1173; from
+  // Cin = 256 up the CTA-pair path with 4 input boxes per stage wins (conv3_2 1426 vs 1287, conv4_2 1445 vs 917).
+  int colbox = (R == 3 && S == 3 && pad == 1 && x.C <= 128 && block_n_in <= 0) ? 1 : 0;
+  { const char* e = getenv("DBX_COLBOX");
+    if (e && e[0] == '0') colbox = 0;
+    if (e && e[0] == '1' && R == 3 && S == 3 && pad == 1 && block_n_in <= 0) colbox = 1; }
   CUtensorMap tmDy, tmX;
   int rc;
   if (colbox) {
@@ -850,7 +856,7 @@ int conv_wgrad(const Act& x, const Act& dy, int R, int S, int pad, float* dw, in
   p.cin_blocks = x.C / 64; p.q_total = q_total; p.nb = block_n / 64; p.block_n = block_n;
   p.m_tiles = (dy.C + 127) / 128; p.q_tiles = (q_total + p.nb - 1) / p.nb;
   p.colbox = colbox;
-  if (colbox) { p.q_tiles = 3; p.nb = 1; }  // q-tile = filter column s
+  if (colbox) { p.q_tiles = 3 * p.cin_blocks; p.nb = 1; }  // q-tile = (channel slice, filter column s)
   p.boxes_total = t.count();
   // CTA pairs (cta_group::2) share the shifted-input boxes: worth it from two output-channel tiles up
   int cta2 = (!colbox && p.m_tiles >= 2 && block_n == 256 && num_sms() >= 2) ? 1 : 0;
