@@ -89,6 +89,16 @@ int dbx_maxpool2x2_bwd(const void* y, int N, int H, int W, int C, int y_cs, int 
   return maxpool2x2_bwd(mk_act(y, N, H, W, C, y_cs, y_coff), mk_act(dp, N, H / 2, W / 2, C, dp_cs, dp_coff),
                         add ? &a : nullptr, mk_act(dy, N, H, W, C, dy_cs, dy_coff), (cudaStream_t)stream);
 }
+int dbx_maxpool2x2_fwd_idx(const void* y, int N, int H, int W, int C, int y_cs, int y_coff, void* out, int o_cs,
+                           int o_coff, void* idx, void* stream) {
+  return maxpool2x2_fwd(mk_act(y, N, H, W, C, y_cs, y_coff), mk_act(out, N, H / 2, W / 2, C, o_cs, o_coff),
+                        (cudaStream_t)stream, idx);
+}
+int dbx_maxpool2x2_bwd_idx(const void* p, int N, int H, int W, int C, int p_cs, int p_coff, const void* dp, int dp_cs,
+                           int dp_coff, const void* idx, void* dy, int dy_cs, int dy_coff, float* db, void* stream) {
+  return maxpool2x2_bwd_idx(mk_act(p, N, H / 2, W / 2, C, p_cs, p_coff), mk_act(dp, N, H / 2, W / 2, C, dp_cs, dp_coff),
+                            idx, mk_act(dy, N, H, W, C, dy_cs, dy_coff), (cudaStream_t)stream, db);
+}
 int dbx_upsample_bilinear_fwd(const void* in, int N, int h, int w, int C, int in_cs, int in_coff, void* out, int H,
                               int W, int o_cs, int o_coff, void* stream) {
   return upsample_bilinear_fwd(mk_act(in, N, h, w, C, in_cs, in_coff), mk_act(out, N, H, W, C, o_cs, o_coff),

@@ -76,7 +76,10 @@ int conv_wgrad(const Act& x, const Act& dy, int R, int S, int pad, float* dw, in
 
 // ---- HBM-bound kernels (dbx_elementwise.cu)
 int im2col3x3_c3(const float* x, void* out, int N, int H, int W, int write_pad, cudaStream_t st);
-int maxpool2x2_fwd(const Act& y, const Act& o, cudaStream_t st);
+// idx (optional): u16 per (pooled pixel, 8-channel vector), 2 bits per element = position of the first maximum
+int maxpool2x2_fwd(const Act& y, const Act& o, cudaStream_t st, void* idx = nullptr);
+// backward from that map and the pooled activation p (no full-resolution read): dy = relu'(y) * unpool(dp)
+int maxpool2x2_bwd_idx(const Act& p, const Act& dp, const void* idx, const Act& dy, cudaStream_t st, float* db = nullptr);
 // db (optional, both): db[c] += column sums of the gradient written (bias gradient of the conv that produced y)
 int maxpool2x2_bwd(const Act& y, const Act& dp, const Act* add, const Act& dy, cudaStream_t st, float* db = nullptr);
 int upsample_bilinear_fwd(const Act& in, const Act& out, cudaStream_t st);

@@ -23,6 +23,8 @@ __device__ __forceinline__ bf16* at(const Act& a, int n, int y, int x, int c) {
   return reinterpret_cast<bf16*>(a.ptr) + (((size_t)n * a.H + y) * a.W + x) * a.cs + a.coff + c;
 }
 
+__device__ __forceinline__ void fold_bias_partials(const float* acc, int cc, float* __restrict__ db, float* red);
+
 // ------------------------------------------------------------------------------------------------ ingest
 // X fp32 NCHW [N,3,H,W] -> bf16 [N,H,W,64]: channel (r*3+s)*3+c holds X[n,c,y+r-1,x+s-1] (zero outside), channels
 // 27..63 are zero.  conv1_1 (DenseBox.py:185) then is a K=64 1x1 GEMM on the tensor cores.
@@ -65,7 +67,10 @@ int im2col3x3_c3(const float* x, void* out, int N, int H, int W, int write_pad, 
 }
 
 // ------------------------------------------------------------------------------------------------ max-pool 2x2
-__global__ void maxpool2x2_fwd_kernel(Act y, Act o) {
+// idx (optional): 2 bits per pooled element = position (2*dy+dx) of the FIRST maximum of its window, 16 bits per
+// (pooled pixel, 8-channel vector).  With it the backward pass needs the pooled map (15 + 15 bytes... one quarter of
+// the bytes) instead of re-reading the full-resolution activation to find the arg-max and its ReLU mask.
+__global__ void maxpool2x2_fwd_kernel(Act y, Act o, unsigned short* __restrict__ idx_out) {
   const int cc = o.C / 8;
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t total = (size_t)o.N * o.H * o.W * cc;
@@ -73,24 +78,79 @@ __global__ void maxpool2x2_fwd_kernel(Act y, Act o) {
   const int c = (int)(idx % cc) * 8;
   const size_t pix = idx / cc;
   const int ox = (int)(pix % o.W), oy = (int)((pix / o.W) % o.H), n = (int)(pix / ((size_t)o.W * o.H));
-  float a[8], b[8];
+  float a[8], b[8], c2[8], d[8];
   unpack8(ldg16(at(y, n, 2 * oy, 2 * ox, c)), a);
   unpack8(ldg16(at(y, n, 2 * oy, 2 * ox + 1, c)), b);
+  unpack8(ldg16(at(y, n, 2 * oy + 1, 2 * ox, c)), c2);
+  unpack8(ldg16(at(y, n, 2 * oy + 1, 2 * ox + 1, c)), d);
+  unsigned int bits = 0u;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) a[j] = fmaxf(a[j], b[j]);
-  unpack8(ldg16(at(y, n, 2 * oy + 1, 2 * ox, c)), b);
-#pragma unroll
-  for (int j = 0; j < 8; ++j) a[j] = fmaxf(a[j], b[j]);
-  unpack8(ldg16(at(y, n, 2 * oy + 1, 2 * ox + 1, c)), b);
-#pragma unroll
-  for (int j = 0; j < 8; ++j) a[j] = fmaxf(a[j], b[j]);
+  for (int j = 0; j < 8; ++j) {
+    unsigned int arg = 0u; float m = a[j];
+    if (b[j] > m) { m = b[j]; arg = 1u; }
+    if (c2[j] > m) { m = c2[j]; arg = 2u; }
+    if (d[j] > m) { m = d[j]; arg = 3u; }
+    a[j] = m;
+    bits |= arg << (2 * j);
+  }
   *reinterpret_cast<uint4*>(at(o, n, oy, ox, c)) = pack8(a);
+  if (idx_out) idx_out[idx] = (unsigned short)bits;
 }
 
-int maxpool2x2_fwd(const Act& y, const Act& o, cudaStream_t st) {
+int maxpool2x2_fwd(const Act& y, const Act& o, cudaStream_t st, void* idx) {
   if (y.H != 2 * o.H || y.W != 2 * o.W || y.C != o.C || y.N != o.N || y.C % 8) return DBX_ERR_ARG;
   const size_t total = (size_t)o.N * o.H * o.W * (o.C / 8);
-  maxpool2x2_fwd_kernel<<<grid_for(total, 256), 256, 0, st>>>(y, o);
+  maxpool2x2_fwd_kernel<<<grid_for(total, 256), 256, 0, st>>>(y, o, (unsigned short*)idx);
+  return (int)cudaGetLastError();
+}
+
+// Backward from the compact arg-max map written by maxpool2x2_fwd(idx): dy[k] = (k == arg && p > 0) ? dp : 0 — the
+// ReLU mask of the producing conv only matters at the arg-max, whose value IS the pooled value p.  Reads 16 + 16 + 2
+// bytes and writes 64 per item (the full-resolution read of y, 64 bytes, is gone).  db as in maxpool2x2_bwd.
+__global__ void __launch_bounds__(256) maxpool2x2_bwd_idx_kernel(Act p, Act dp, const unsigned short* __restrict__ idx_in,
+                                                                 Act dy, float* __restrict__ db) {
+  __shared__ float red[256 * 8];
+  const int cc = dp.C / 8;
+  const size_t total = (size_t)dp.N * dp.H * dp.W * cc;
+  float bsum[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) bsum[j] = 0.f;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % cc) * 8;
+    const size_t pix = idx / cc;
+    const int ox = (int)(pix % dp.W), oy = (int)((pix / dp.W) % dp.H), n = (int)(pix / ((size_t)dp.W * dp.H));
+    float pv[8], g[8];
+    unpack8(ldg16(at(p, n, oy, ox, c)), pv);
+    const uint4 gq = ldg16(at(dp, n, oy, ox, c));
+    unpack8(gq, g);
+    const unsigned int bits = idx_in[idx];
+    float o[4][8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const unsigned int arg = (bits >> (2 * j)) & 3u;
+      const float v = pv[j] > 0.f ? g[j] : 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) o[k][j] = (unsigned int)k == arg ? v : 0.f;
+      bsum[j] += v;  // dp is bf16 already: what is stored equals v exactly
+    }
+    *reinterpret_cast<uint4*>(at(dy, n, 2 * oy, 2 * ox, c)) = pack8(o[0]);
+    *reinterpret_cast<uint4*>(at(dy, n, 2 * oy, 2 * ox + 1, c)) = pack8(o[1]);
+    *reinterpret_cast<uint4*>(at(dy, n, 2 * oy + 1, 2 * ox, c)) = pack8(o[2]);
+    *reinterpret_cast<uint4*>(at(dy, n, 2 * oy + 1, 2 * ox + 1, c)) = pack8(o[3]);
+  }
+  if (db) fold_bias_partials(bsum, cc, db, red);
+}
+
+int maxpool2x2_bwd_idx(const Act& p, const Act& dp, const void* idx, const Act& dy, cudaStream_t st, float* db) {
+  if (!idx || dy.H != 2 * dp.H || dy.W != 2 * dp.W || dy.C != dp.C || p.C != dp.C || p.H != dp.H || p.W != dp.W ||
+      dp.C % 8)
+    return DBX_ERR_ARG;
+  const int cc = dp.C / 8;
+  if (256 % cc) return DBX_ERR_ARG;
+  const size_t total = (size_t)dp.N * dp.H * dp.W * cc;
+  int blocks = grid_for(total, 256);
+  if (blocks > 16 * num_sms()) blocks = 16 * num_sms();
+  maxpool2x2_bwd_idx_kernel<<<blocks, 256, 0, st>>>(p, dp, (const unsigned short*)idx, dy, db);
   return (int)cudaGetLastError();
 }
 

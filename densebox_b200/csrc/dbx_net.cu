@@ -198,6 +198,8 @@ struct Net {
       add_buf("g32", flat_n * 4);
       add_buf("v32", flat_n * 4);
       add_buf("drop", px4 * 512 * nh * 2);
+      add_buf("pi1", px2 * 8 * 2);    // arg-max maps of pool1 / pool2: u16 per (pooled pixel, 8-channel vector)
+      add_buf("pi2", px4 * 16 * 2);
       add_buf("d_head", px4 * 64 * 2);
       add_buf("d_hd", px4 * 512 * nh * 2);
       add_buf("d_fusion", px4 * 768 * 2);
@@ -354,10 +356,10 @@ struct Net {
     DBX_K("im2col", 0.0, im2col3x3_c3(x, col0.ptr, N, H, W, 0, st));
     DBX_TRY(conv(col0, "conv1_1", 1, 0, a11, true, nullptr, 0, 0, false, 0, st));
     DBX_TRY(conv(a11, "conv1_2", 3, 1, a12, true, nullptr, 0, 0, false, 0, st));
-    DBX_K("pool_fwd", 0.0, maxpool2x2_fwd(a12, p1, st));
+    DBX_K("pool_fwd", 0.0, maxpool2x2_fwd(a12, p1, st, train ? buf("pi1") : nullptr));
     DBX_TRY(conv(p1, "conv2_1", 3, 1, a21, true, nullptr, 0, 0, false, 0, st));
     DBX_TRY(conv(a21, "conv2_2", 3, 1, a22, true, nullptr, 0, 0, false, 0, st));
-    DBX_K("pool_fwd", 0.0, maxpool2x2_fwd(a22, p2, st));
+    DBX_K("pool_fwd", 0.0, maxpool2x2_fwd(a22, p2, st, train ? buf("pi2") : nullptr));
     DBX_TRY(conv(p2, "conv3_1", 3, 1, a31, true, nullptr, 0, 0, false, 0, st));
     DBX_TRY(conv(a31, "conv3_2", 3, 1, a32, true, nullptr, 0, 0, false, 0, st));
     DBX_TRY(conv(a32, "conv3_4", 3, 1, a34, true, nullptr, 0, 0, false, 0, st));  // conv3_3 skipped (:193-195)
@@ -431,6 +433,8 @@ struct Net {
     // bias gradients come out of the epilogue of the launch that produces dZ (DBX_FUSE_BIAS=0: stand-alone colsum)
     bool fuse = true;
     { const char* e = getenv("DBX_FUSE_BIAS"); if (e && e[0] == '0') fuse = false; }
+    bool pool_idx = true;
+    { const char* e = getenv("DBX_POOL_IDX"); if (e && e[0] == '0') pool_idx = false; }
     bool fuse_short = false;
     { const char* e = getenv("DBX_FUSE_BIAS_SHORT"); if (e && e[0] == '1') fuse_short = fuse; }
     const int h2 = H / 2, w2 = W / 2, h4 = H / 4, w4 = W / 4, h8 = H / 8, w8 = W / 8;
@@ -515,7 +519,9 @@ struct Net {
     DBX_TRY(wgrad(p2, d_a31, "conv3_1", 3, 1, st, fuse));
     DBX_TRY(dgrad(d_a31, "conv3_1", 3, 1, d_p2, nullptr, st));
     // conv2 block
-    DBX_K("pool_bwd", 0.0, maxpool2x2_bwd(a22, d_p2, nullptr, d_a22, st, fuse ? gb_of("conv2_2") : nullptr));
+    // pool2 / pool1 backward read the pooled map + the 2-bit arg-max map of the forward pass instead of a22 / a12
+    if (pool_idx) DBX_K("pool_bwd", 0.0, maxpool2x2_bwd_idx(p2, d_p2, buf("pi2"), d_a22, st, fuse ? gb_of("conv2_2") : nullptr));
+    else DBX_K("pool_bwd", 0.0, maxpool2x2_bwd(a22, d_p2, nullptr, d_a22, st, fuse ? gb_of("conv2_2") : nullptr));
     DBX_TRY(wgrad(a21, d_a22, "conv2_2", 3, 1, st, fuse));
     // conv2_2 / conv1_2 data gradients: the K loop is too short to hide the extra epilogue work (measured: +0.059 ms
     // on dgrad conv2_2 against 0.027 ms for the stand-alone pass), their bias gradients stay with wgrad()
@@ -523,7 +529,8 @@ struct Net {
     DBX_TRY(wgrad(p1, d_a21, "conv2_1", 3, 1, st, fuse_short));
     DBX_TRY(dgrad(d_a21, "conv2_1", 3, 1, d_p1, nullptr, st));
     // conv1 block
-    DBX_K("pool_bwd", 0.0, maxpool2x2_bwd(a12, d_p1, nullptr, d_a12, st, fuse ? gb_of("conv1_2") : nullptr));
+    if (pool_idx) DBX_K("pool_bwd", 0.0, maxpool2x2_bwd_idx(p1, d_p1, buf("pi1"), d_a12, st, fuse ? gb_of("conv1_2") : nullptr));
+    else DBX_K("pool_bwd", 0.0, maxpool2x2_bwd(a12, d_p1, nullptr, d_a12, st, fuse ? gb_of("conv1_2") : nullptr));
     DBX_TRY(wgrad(a11, d_a12, "conv1_2", 3, 1, st, fuse));
     DBX_TRY(dgrad(d_a12, "conv1_2", 3, 1, d_a11, &a11, st, fuse_short ? "conv1_1" : nullptr));
     DBX_TRY(wgrad(col0, d_a11, "conv1_1", 1, 0, st, fuse_short));

@@ -85,6 +85,24 @@ def maxpool2x2_fwd(y, out):
     return out
 
 
+def maxpool2x2_fwd_idx(y, out, idx):
+    """Pooling + compact arg-max map idx (int16 tensor [N, H/2, W/2, C/8])."""
+    y, out = _v(y), _v(out)
+    assert idx.dtype == torch.int16 and idx.is_contiguous() and idx.numel() == out.N * out.H * out.W * (out.C // 8)
+    check(lib().dbx_maxpool2x2_fwd_idx(ptr(y.buf), c_int(y.N), c_int(y.H), c_int(y.W), c_int(y.C), c_int(y.cs),
+                                       c_int(y.coff), *_vargs(out), ptr(idx), stream_ptr()), "maxpool2x2_fwd_idx")
+    return out
+
+
+def maxpool2x2_bwd_idx(p, dp, idx, dy, db=None):
+    """Backward from the pooled activation + arg-max map (no full-resolution read); db += column sums of dy."""
+    p, dp, dy = _v(p), _v(dp), _v(dy)
+    check(lib().dbx_maxpool2x2_bwd_idx(ptr(p.buf), c_int(dy.N), c_int(dy.H), c_int(dy.W), c_int(dy.C), c_int(p.cs),
+                                       c_int(p.coff), *_vargs(dp), ptr(idx), *_vargs(dy), ptr(db), stream_ptr()),
+          "maxpool2x2_bwd_idx")
+    return dy
+
+
 def maxpool2x2_bwd(y, dp, dy, add=None):
     y, dp, dy = _v(y), _v(dp), _v(dy)
     a = _vargs(_v(add)) if add is not None else [ptr(None), c_int(0), c_int(0)]

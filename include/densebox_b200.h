@@ -46,6 +46,14 @@ int dbx_maxpool2x2_fwd(const void* y, int N, int H, int W, int C, int y_cs, int 
 int dbx_maxpool2x2_bwd(const void* y, int N, int H, int W, int C, int y_cs, int y_coff, const void* dp, int dp_cs,
                        int dp_coff, const void* add, int add_cs, int add_coff, void* dy, int dy_cs, int dy_coff,
                        void* stream);
+/* Same pooling, plus a compact arg-max map idx (u16 per pooled pixel and 8-channel vector, 2 bits per element =
+ * position 2*dy+dx of the first maximum); and the backward that uses it together with the POOLED activation p instead
+ * of re-reading the full-resolution y: dy[k] = (k == arg && p > 0) ? dp : 0; db (optional) += column sums of dy (bias
+ * gradient of the conv that produced y).  H, W are the full-resolution extent in both. */
+int dbx_maxpool2x2_fwd_idx(const void* y, int N, int H, int W, int C, int y_cs, int y_coff, void* out, int o_cs,
+                           int o_coff, void* idx, void* stream);
+int dbx_maxpool2x2_bwd_idx(const void* p, int N, int H, int W, int C, int p_cs, int p_coff, const void* dp, int dp_cs,
+                           int dp_coff, const void* idx, void* dy, int dy_cs, int dy_coff, float* db, void* stream);
 int dbx_upsample_bilinear_fwd(const void* in, int N, int h, int w, int C, int in_cs, int in_coff, void* out, int H,
                               int W, int o_cs, int o_coff, void* stream);
 int dbx_upsample_bilinear_bwd(const void* dout, int N, int H, int W, int C, int d_cs, int d_coff, const void* relu_y,

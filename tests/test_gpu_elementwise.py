@@ -94,3 +94,29 @@ def test_colsum(C):
     ops.colsum(ops.View(buf, C, 0), db)
     ref = 1.0 + buf[..., :C].float().sum(dim=(0, 1, 2))
     assert (db - ref).abs().max().item() <= 1e-3 * ref.abs().max().item()
+
+
+def test_maxpool_bwd_from_argmax_map_matches_full_resolution_backward():
+    """maxpool2x2_fwd_idx + maxpool2x2_bwd_idx (pooled map + 2-bit arg-max map) must reproduce maxpool2x2_fwd +
+    maxpool2x2_bwd (which re-reads the full-resolution activation) bit for bit, including ties (post-ReLU zeros:
+    first maximum in scan order) and the fused bias-gradient column sums."""
+    from densebox_b200 import ops
+    torch.manual_seed(0)
+    N, H, W, C = 3, 24, 16, 128
+    y = torch.relu(torch.randn(N, H, W, C, device="cuda")).to(torch.bfloat16)  # ~50 % exact zeros -> many ties
+    y[:, ::2, ::2] = y[:, 1::2, 1::2]                                          # and equal non-zero maxima
+    dp = torch.randn(N, H // 2, W // 2, C, device="cuda").to(torch.bfloat16)
+    out_a = torch.empty(N, H // 2, W // 2, C, dtype=torch.bfloat16, device="cuda")
+    out_b = torch.empty_like(out_a)
+    idx = torch.empty(N, H // 2, W // 2, C // 8, dtype=torch.int16, device="cuda")
+    ops.maxpool2x2_fwd(y, out_a)
+    ops.maxpool2x2_fwd_idx(y, out_b, idx)
+    assert torch.equal(out_a, out_b)
+    dy_a = torch.empty_like(y)
+    dy_b = torch.full_like(y, 7.0)
+    ops.maxpool2x2_bwd(y, dp, dy_a)
+    db = torch.zeros(C, device="cuda")
+    ops.maxpool2x2_bwd_idx(out_b, dp, idx, dy_b, db=db)
+    assert torch.equal(dy_a, dy_b)
+    ref = dy_a.float().sum((0, 1, 2))
+    assert (db - ref).abs().max().item() <= 1e-4 * ref.abs().max().item()
