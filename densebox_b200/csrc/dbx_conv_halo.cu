@@ -68,7 +68,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
   if (warp == 1) { tmem_alloc(&tmem_base_s, p.tmem_cols); tmem_relinquish(); }
   float* csum = p.colsum ? reinterpret_cast<float*>(smem + p.csum_off) : nullptr;
-  if (csum) for (int c = threadIdx.x; c < p.cout; c += kHaloThreads) csum[c] = 0.f;
+  if (csum) for (int c = threadIdx.x; c < 8 * p.cout; c += kHaloThreads) csum[c] = 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -206,7 +206,12 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   tc_fence_before();
   __syncthreads();
   if (csum)
-    for (int c = threadIdx.x; c < p.cout; c += kHaloThreads) { const float v = csum[c]; if (v != 0.f) atomicAdd(p.colsum + c, v); }
+    for (int c = threadIdx.x; c < p.cout; c += kHaloThreads) {
+      float v = 0.f;
+#pragma unroll
+      for (int g = 0; g < 8; ++g) v += csum[g * p.cout + c];
+      if (v != 0.f) atomicAdd(p.colsum + c, v);
+    }
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem, p.tmem_cols); }
 }
 
@@ -222,7 +227,7 @@ int conv3x3_halo(const Act& x, const void* wk, const Act& out, const ConvEpilogu
   if (x.C % 64 || x.C > 128 || out.C % 64 || out.H != x.H || out.W != x.W || out.N != x.N) return DBX_ERR_ARG;
   if (epi.aux_mode && (!epi.aux || epi.aux_cs % 8 || epi.aux_coff % 8)) return DBX_ERR_ARG;
   if (epi.colsum && epi.bias) return DBX_ERR_ARG;
-  const int csum_bytes = epi.colsum ? (out.C * 4 + 1023) / 1024 * 1024 : 0;
+  const int csum_bytes = epi.colsum ? (8 * out.C * 4 + 1023) / 1024 * 1024 : 0;
   HaloParams p{};
   p.block_n = out.C >= 128 ? 128 : 64;
   p.tiles_w = (out.W + 7) / 8; p.tiles_h = (out.H + 15) / 16;

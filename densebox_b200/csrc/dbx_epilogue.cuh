@@ -33,7 +33,8 @@ struct EpiArgs {
   int tw, th, box_rows;                 // pixel box of one tile (rows = tw*th*tn <= 128)
   int out_W, out_H;                     // aux_mode 3: element index of the dropped activation
   const unsigned long long* rng; int rng_channels;
-  float* csum = nullptr;                // smem fp32 [cout]: running column sums of everything this CTA stored (or null)
+  float* csum = nullptr;                // smem fp32 [8][cout] (one copy per row group): running column sums of
+                                        // everything this CTA stored, or null
 };
 
 __device__ __forceinline__ uint32_t bf162_as_u32(__nv_bfloat162 h) { return *reinterpret_cast<uint32_t*>(&h); }
@@ -250,9 +251,11 @@ __device__ __forceinline__ void epilogue_tma(const EpiArgs& e, const CUtensorMap
       if (e.csum) {
         // Column sums of the finished box (bias gradient of the layer below).  Thread t: channel pair t & 31, rows
         // 16 (t >> 5) .. + 15; a warp reads the 32 words of ONE 128-byte row per instruction (conflict-free under
-        // the swizzle).  Rows outside the image are exact zeros (zero-filled operands, no bias).  The box is not
-        // rewritten before every thread has passed the next sub-block's barrier.
-        const int t = (int)threadIdx.x - 64, cp = t & 31, r0 = (t >> 5) * 16;
+        // the swizzle).  Rows outside the image are exact zeros (zero-filled operands, no bias).  Each of the 8 row
+        // groups owns a private copy csum[t >> 5][cout]: plain read-modify-write, no shared-memory float atomics
+        // (those compile to CAS loops and cost +60 % on the short-K layers).  The box is not rewritten before every
+        // thread has passed the next sub-block's barrier.
+        const int t = (int)threadIdx.x - 64, cp = t & 31, rg = t >> 5, r0 = rg * 16;
         float s0 = 0.f, s1 = 0.f;
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
@@ -264,7 +267,12 @@ __device__ __forceinline__ void epilogue_tma(const EpiArgs& e, const CUtensorMap
           }
         }
         const int c = nt * e.block_n + j * 64 + 2 * cp;
-        if (2 * cp < ncols && c < e.cout) { atomicAdd(e.csum + c, s0); atomicAdd(e.csum + c + 1, s1); }
+        if (2 * cp < ncols && c < e.cout) {
+          float2* a = reinterpret_cast<float2*>(e.csum + (size_t)rg * e.cout + c);
+          float2 v = *a;
+          v.x += s0; v.y += s1;
+          *a = v;
+        }
       }
     }
     tc_fence_before();

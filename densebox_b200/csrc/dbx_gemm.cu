@@ -192,7 +192,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     else { tmem_alloc(&tmem_base_s, p.tmem_cols); tmem_relinquish(); }
   }
   float* csum = p.colsum ? reinterpret_cast<float*>(smem + p.csum_off) : nullptr;
-  if (csum) for (int c = threadIdx.x; c < p.cout; c += kFpropThreads) csum[c] = 0.f;
+  if (csum) for (int c = threadIdx.x; c < 8 * p.cout; c += kFpropThreads) csum[c] = 0.f;
   tc_fence_before();
   if constexpr (cta2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
@@ -451,7 +451,12 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   __syncwarp();
   if constexpr (cta2) cluster_sync_all(); else __syncthreads();
   if (csum)  // one global atomic per channel and CTA
-    for (int c = threadIdx.x; c < p.cout; c += kFpropThreads) { const float v = csum[c]; if (v != 0.f) atomicAdd(p.colsum + c, v); }
+    for (int c = threadIdx.x; c < p.cout; c += kFpropThreads) {
+      float v = 0.f;
+#pragma unroll
+      for (int g = 0; g < 8; ++g) v += csum[g * p.cout + c];
+      if (v != 0.f) atomicAdd(p.colsum + c, v);
+    }
   if (warp == 1) {
     tc_fence_after();
     if constexpr (cta2) tmem_dealloc_2sm(tmem, p.tmem_cols); else tmem_dealloc(tmem, p.tmem_cols);
@@ -568,14 +573,14 @@ int conv_fprop(const Act& x, const void* wk, int R, int S, int pad, const Act& o
   if (p.stages > kMaxStages) p.stages = kMaxStages;
   { const char* e = getenv("DBX_STAGES"); if (e && atoi(e) >= 2 && atoi(e) < p.stages) p.stages = atoi(e); }
   if (p.stages < 2) return DBX_ERR_ARG;
-  // fused column sums (bias gradient of the layer below): need cout floats of spare shared memory behind the ring
+  // fused column sums (bias gradient of the layer below): need 8 x cout floats of spare shared memory behind the ring
   bool colsum_after = false;
   p.colsum = nullptr; p.csum_off = 0;
   if (epi.colsum) {
     if (epi.bias) return DBX_ERR_ARG;
     const int used = p.stages * stage_bytes + ring;
     const char* e = getenv("DBX_FUSED_COLSUM");
-    if (tma_epi && used + out.C * 4 <= kSmemBudget && !(e && e[0] == '0')) { p.colsum = epi.colsum; p.csum_off = used; }
+    if (tma_epi && out.C % 2 == 0 && used + 8 * out.C * 4 <= kSmemBudget && !(e && e[0] == '0')) { p.colsum = epi.colsum; p.csum_off = used; }
     else colsum_after = true;   // no room (or fp32 output): same result from the stand-alone kernel after the launch
   }
   p.idesc = umma_idesc_bf16(cta2 ? 256 : 128, block_n, 0, 0);
@@ -599,7 +604,7 @@ int conv_fprop(const Act& x, const void* wk, int R, int S, int pad, const Act& o
   }();
   if (attr_rc) return attr_rc;
   const FpropFn fn = fns[cta2 ? 1 : 0][colbox ? 3 : (p.kps == 4 ? 2 : (p.kps == 2 ? 1 : 0))];
-  const size_t smem = (size_t)p.stages * stage_bytes + ring + (p.colsum ? (size_t)out.C * 4 : 0) + 1024;
+  const size_t smem = (size_t)p.stages * stage_bytes + ring + (p.colsum ? (size_t)8 * out.C * 4 : 0) + 1024;
   cudaLaunchConfig_t cfg{};
   cfg.blockDim = dim3(kFpropThreads);
   cfg.dynamicSmemBytes = smem;

@@ -435,6 +435,9 @@ struct Net {
     { const char* e = getenv("DBX_FUSE_BIAS"); if (e && e[0] == '0') fuse = false; }
     bool pool_idx = true;
     { const char* e = getenv("DBX_POOL_IDX"); if (e && e[0] == '0') pool_idx = false; }
+    // The two short-K data gradients (conv2_2, conv1_2) are paced by their epilogue: the column sums cost them
+    // +0.047 / +0.05 ms (measured, with or without shared-memory atomics) against 0.027 / 0.05 ms for the stand-alone
+    // pass on the side stream, so their bias gradients stay with wgrad().  DBX_FUSE_BIAS_SHORT=1 fuses them too.
     bool fuse_short = false;
     { const char* e = getenv("DBX_FUSE_BIAS_SHORT"); if (e && e[0] == '1') fuse_short = fuse; }
     const int h2 = H / 2, w2 = W / 2, h4 = H / 4, w4 = W / 4, h8 = H / 8, w8 = W / 8;
@@ -523,8 +526,6 @@ struct Net {
     if (pool_idx) DBX_K("pool_bwd", 0.0, maxpool2x2_bwd_idx(p2, d_p2, buf("pi2"), d_a22, st, fuse ? gb_of("conv2_2") : nullptr));
     else DBX_K("pool_bwd", 0.0, maxpool2x2_bwd(a22, d_p2, nullptr, d_a22, st, fuse ? gb_of("conv2_2") : nullptr));
     DBX_TRY(wgrad(a21, d_a22, "conv2_2", 3, 1, st, fuse));
-    // conv2_2 / conv1_2 data gradients: the K loop is too short to hide the extra epilogue work (measured: +0.059 ms
-    // on dgrad conv2_2 against 0.027 ms for the stand-alone pass), their bias gradients stay with wgrad()
     DBX_TRY(dgrad(d_a22, "conv2_2", 3, 1, d_a21, &a21, st, fuse_short ? "conv2_1" : nullptr));
     DBX_TRY(wgrad(p1, d_a21, "conv2_1", 3, 1, st, fuse_short));
     DBX_TRY(dgrad(d_a21, "conv2_1", 3, 1, d_p1, nullptr, st));
