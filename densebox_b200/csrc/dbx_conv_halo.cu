@@ -23,6 +23,7 @@ static constexpr int kHaloSmem = 230400;
 
 struct HaloParams {
   int tiles_w, tiles_h, m_tiles, n_tiles, block_n;
+  FastDiv fd_mt, fd_tw, fd_twh;   // division by m_tiles, tiles_w, tiles_w * tiles_h
   int cin_blocks, cin;     // K per tap = cin (multiple of 64)
   int cout;
   int resident;            // whole filter resident in smem (n_tiles == 1)
@@ -85,9 +86,9 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     __syncwarp();
     for (int t = blockIdx.x; t < total; t += gridDim.x) {
-      const int nt = t / p.m_tiles, mt = t % p.m_tiles;
-      const int w0 = (mt % p.tiles_w) * 8, h0 = ((mt / p.tiles_w) % p.tiles_h) * 16;
-      const int n0 = mt / (p.tiles_w * p.tiles_h);
+      const int nt = p.fd_mt.div(t), mt = t - nt * p.m_tiles;
+      const int n0 = p.fd_twh.div(mt), rem = mt - n0 * (p.tiles_w * p.tiles_h);
+      const int hq = p.fd_tw.div(rem), w0 = (rem - hq * p.tiles_w) * 8, h0 = hq * 16;
       for (int cb = 0; cb < p.cin_blocks; ++cb)
         for (int s = 0; s < 3; ++s) {
           mbar_wait_a(aempty0 + 8u * as, aph ^ 1);
@@ -197,9 +198,11 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int my_tiles = (int)blockIdx.x < total ? (total - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
     auto tile_of = [&](int it, int& nt, int& w0, int& h0, int& n0) {
       const int t = (int)blockIdx.x + it * (int)gridDim.x;
-      const int mt = t % p.m_tiles;
-      nt = t / p.m_tiles;
-      w0 = (mt % p.tiles_w) * 8; h0 = ((mt / p.tiles_w) % p.tiles_h) * 16; n0 = mt / (p.tiles_w * p.tiles_h);
+      nt = p.fd_mt.div(t);
+      const int mt = t - nt * p.m_tiles;
+      n0 = p.fd_twh.div(mt);
+      const int rem = mt - n0 * (p.tiles_w * p.tiles_h), hq = p.fd_tw.div(rem);
+      w0 = (rem - hq * p.tiles_w) * 8; h0 = hq * 16;
     };
     epilogue_tma<false>(ea, &tmO, &tmX, ring, aux_bar, tfull_bar, tempty_bar, tmem, my_tiles, tile_of);
   }
@@ -234,6 +237,7 @@ int conv3x3_halo(const Act& x, const void* wk, const Act& out, const ConvEpilogu
   p.m_tiles = p.tiles_w * p.tiles_h * out.N;
   p.n_tiles = (out.C + p.block_n - 1) / p.block_n;
   p.cin_blocks = x.C / 64; p.cin = x.C; p.cout = out.C;
+  p.fd_mt = FastDiv::make(p.m_tiles); p.fd_tw = FastDiv::make(p.tiles_w); p.fd_twh = FastDiv::make(p.tiles_w * p.tiles_h);
   const int b_tile = p.block_n * 128;
   const int kb_per_tile = 9 * p.cin_blocks;
   p.nsb = (p.block_n + 63) / 64;

@@ -114,9 +114,10 @@ __device__ __forceinline__ void epilogue_tma(const EpiArgs& e, const CUtensorMap
     tile_of(it, nt, w0, h0, n0);
     const int buf = it & 1; const uint32_t use = (uint32_t)(it >> 1);
     // element index of this row's channel 0 in the dropped activation (aux_mode 3)
-    const unsigned long long e_row =
-        (((unsigned long long)(n0 + r_n) * e.out_H + (h0 + r_h)) * e.out_W + (w0 + r_w)) *
-        (unsigned long long)e.rng_channels;
+    unsigned long long e_row = 0ull;
+    if (e.aux_mode == 3)
+      e_row = (((unsigned long long)(n0 + r_n) * e.out_H + (h0 + r_h)) * e.out_W + (w0 + r_w)) *
+              (unsigned long long)e.rng_channels;
     mbar_wait(&tfull_bar[buf], use & 1);
     tc_fence_after();
     const uint32_t taddr = tmem + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(buf * e.block_n);

@@ -122,6 +122,7 @@ struct FpropParams {
   int R, S, pad;
   int cin, cin_blocks;
   int m_tiles, n_tiles, block_n;
+  FastDiv fd_nt, fd_tw, fd_twh;   // division by n_tiles, tiles_w, tiles_w * tiles_h
   int cout;
   float* colsum; int csum_off;  // fused bias gradient: global fp32 [cout], smem offset of the per-CTA partial sums
   int debug;               // measurement only (DBX_DEBUG): 1 = no TMA loads, 2 = no MMAs — results are garbage
@@ -176,7 +177,11 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   // activations stream from HBM once (the weights of all channel tiles stay L2-resident).  With the pixel tile
   // fastest the 1x1 head GEMM re-read its 177 MB input once per channel tile (ncu: 709 MB of DRAM reads).
 #define DBX_UNIT_TILE(u, nt, mt) \
-  const int nt = (u) % p.n_tiles, mt = cta2 ? 2 * ((u) / p.n_tiles) + (int)rank : (u) / p.n_tiles
+  const int mq_##mt = p.fd_nt.div(u), nt = (u) - mq_##mt * p.n_tiles, mt = cta2 ? 2 * mq_##mt + (int)rank : mq_##mt
+  // pixel-tile index -> box origin (in tiles): n = mt / (tiles_w * tiles_h), h = rest / tiles_w, w = rest % tiles_w
+#define DBX_TILE_ORIGIN(mt, tw_i, th_i, tn_i) \
+  const int tn_i = p.fd_twh.div(mt), rem_##tn_i = (mt) - tn_i * (p.tiles_w * p.tiles_h), \
+            th_i = p.fd_tw.div(rem_##tn_i), tw_i = rem_##tn_i - th_i * p.tiles_w
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
@@ -218,9 +223,8 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     int stage = 0; uint32_t phase = 0;
     for (int u = u0; u < total; u += ustep) {
       DBX_UNIT_TILE(u, nt, mt);
-      const int w0 = (mt % p.tiles_w) * p.tw - p.pad;
-      const int h0 = ((mt / p.tiles_w) % p.tiles_h) * p.th - p.pad;
-      const int n0 = (mt / (p.tiles_w * p.tiles_h)) * p.tn;
+      DBX_TILE_ORIGIN(mt, twi, thi, tni);
+      const int w0 = twi * p.tw - p.pad, h0 = thi * p.th - p.pad, n0 = tni * p.tn;
       const int brow = nt * p.block_n + (int)(rank * b_rows) * (cta2 ? 1 : 0);
       if constexpr (colbox) {
         for (int cb = 0; cb < p.cin_blocks; ++cb)
@@ -370,8 +374,8 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       auto tile_of = [&](int it, int& nt, int& w0, int& h0, int& n0) {
         DBX_UNIT_TILE(u0 + it * ustep, nt_, mt_);
         nt = nt_;
-        w0 = (mt_ % p.tiles_w) * p.tw; h0 = ((mt_ / p.tiles_w) % p.tiles_h) * p.th;
-        n0 = (mt_ / (p.tiles_w * p.tiles_h)) * p.tn;
+        DBX_TILE_ORIGIN(mt_, twi, thi, tni);
+        w0 = twi * p.tw; h0 = thi * p.th; n0 = tni * p.tn;
       };
       epilogue_tma<cta2>(ea, &tmO, &tmX, smem + (size_t)p.stages * stage_bytes, aux_bar, tfull_bar, tempty_bar, tmem,
                          my_tiles, tile_of);
@@ -383,9 +387,10 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       for (int u = u0; u < total; u += ustep, ++it) {
         const int buf = it & 1; const uint32_t use = (uint32_t)(it >> 1);
         DBX_UNIT_TILE(u, nt, mt);
-        const int w = (mt % p.tiles_w) * p.tw + row % p.tw;
-        const int h = ((mt / p.tiles_w) % p.tiles_h) * p.th + (row / p.tw) % p.th;
-        const int n = (mt / (p.tiles_w * p.tiles_h)) * p.tn + row / (p.tw * p.th);
+        DBX_TILE_ORIGIN(mt, twi, thi, tni);
+        const int w = twi * p.tw + row % p.tw;
+        const int h = thi * p.th + (row / p.tw) % p.th;
+        const int n = tni * p.tn + row / (p.tw * p.th);
         const bool valid = row < box_rows && w < p.out_W && h < p.out_H && n < p.out_N;
         const size_t pix = ((size_t)n * p.out_H + h) * p.out_W + w;
         mbar_wait(&tfull_bar[buf], use & 1);
@@ -462,6 +467,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if constexpr (cta2) tmem_dealloc_2sm(tmem, p.tmem_cols); else tmem_dealloc(tmem, p.tmem_cols);
   }
 #undef DBX_UNIT_TILE
+#undef DBX_TILE_ORIGIN
 }
 
 static int set_max_smem(const void* fn) {
@@ -545,6 +551,7 @@ int conv_fprop(const Act& x, const void* wk, int R, int S, int pad, const Act& o
   p.R = R; p.S = S; p.pad = pad;
   p.cin = x.C; p.cin_blocks = x.C / 64;
   p.m_tiles = t.count(); p.n_tiles = (out.C + block_n - 1) / block_n; p.block_n = block_n;
+  p.fd_nt = FastDiv::make(p.n_tiles); p.fd_tw = FastDiv::make(p.tiles_w); p.fd_twh = FastDiv::make(p.tiles_w * p.tiles_h);
   p.cout = out.C;
   p.cta2 = cta2;
   const int slot_bytes = colbox ? 18432 + 3 * (cta2 ? block_n / 2 : block_n) * 128

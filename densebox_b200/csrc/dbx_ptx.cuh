@@ -349,6 +349,25 @@ __device__ __forceinline__ uint32_t dropout_bits32(unsigned long long e, unsigne
   return b == 0 ? r.x : (b == 1 ? r.y : (b == 2 ? r.z : r.w));
 }
 
+// ---------------------------------------------------------------- division by a launch constant
+// q = n / d for 0 <= n < 2^31 with the host-computed magic m = floor(2^64 / d) + 1 (exact: n*m/2^64 < n/d + 2^-32).
+// A runtime integer division is ~25 dependent SASS instructions; the tile-index decode of the warp-specialised
+// roles runs once per tile on a single warp and was a third of the epilogue's instruction count (round-1 ncu).
+struct FastDiv {
+  unsigned long long m;
+  int d;
+#ifndef __CUDACC_RTC__
+  static FastDiv make(int d) {
+    FastDiv f; f.d = d < 1 ? 1 : d;
+    f.m = f.d == 1 ? 0ull : (~0ull / (unsigned long long)f.d) + 1ull;  // == floor(2^64/d)+1, or 2^64/d exactly when d is a power of two
+    return f;
+  }
+#endif
+  __device__ __forceinline__ int div(int n) const {
+    return d == 1 ? n : (int)__umul64hi((unsigned long long)(unsigned int)n, m);
+  }
+};
+
 // ---------------------------------------------------------------- misc
 __device__ __forceinline__ float bf16lo(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float bf16hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
