@@ -642,6 +642,7 @@ struct WgradParams {
   int kp;
   int cin_blocks, q_total, nb, block_n;
   int m_tiles, q_tiles, splits, boxes_total, boxes_per_split;
+  FastDiv fd_tps, fd_qt, fd_tw, fd_twh, fd_cb, fd_s;  // division by tiles_per_split, q_tiles, tiles_w, tiles_w * tiles_h, cin_blocks, S
   int cout, ldw;
   float* dw;
   int stages;
@@ -698,17 +699,17 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
     // ===================== TMA producer (warp-uniform schedule walk, one elected lane issues) =====================
     int stage = 0; uint32_t phase = 0;
     for (int t = u0; t < total; t += ustep) {
-      const int split = t / tiles_per_split, rem = t % tiles_per_split;
-      const int m = (cta2 ? 2 : 1) * (rem / p.q_tiles) + (int)rank, q0 = (rem % p.q_tiles) * p.nb;
+      const int split = p.fd_tps.div(t), rem = t - split * tiles_per_split;
+      const int mq = p.fd_qt.div(rem);
+      const int m = (cta2 ? 2 : 1) * mq + (int)rank, q0 = (rem - mq * p.q_tiles) * p.nb;
       int nvalid = p.q_total - q0; if (nvalid > p.nb) nvalid = p.nb;
       const int j0 = (int)rank * nbl;                           // first input box of this CTA
       int jn = nvalid - j0; if (jn > nbl) jn = nbl; if (jn < 0) jn = 0;
       const int b_begin = split * p.boxes_per_split;
       int b_end = b_begin + p.boxes_per_split; if (b_end > p.boxes_total) b_end = p.boxes_total;
       for (int b = b_begin; b < b_end; ++b) {
-        const int w0 = (b % p.tiles_w) * p.tw;
-        const int h0 = ((b / p.tiles_w) % p.tiles_h) * p.th;
-        const int n0 = (b / (p.tiles_w * p.tiles_h)) * p.tn;
+        const int nq = p.fd_twh.div(b), brem = b - nq * (p.tiles_w * p.tiles_h), hq = p.fd_tw.div(brem);
+        const int w0 = (brem - hq * p.tiles_w) * p.tw, h0 = hq * p.th, n0 = nq * p.tn;
         mbar_wait_a(empty0 + 8u * stage, phase ^ 1);
         if (elect_one_sync()) {
           const uint32_t sa = smem_base + (uint32_t)stage * stage_bytes, fb = full0 + 8u * stage;
@@ -730,8 +731,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
             tma_load_4d_a(&tmDy, fb, sa + box_bytes, m * 128 + 64, w0, h0, n0);
           }
           for (int j = 0; j < (p.colbox ? 0 : jn); ++j) {
-            const int qq = q0 + j0 + j, tap = qq / p.cin_blocks, cb = qq % p.cin_blocks;
-            const int r = tap / p.S, s = tap % p.S;
+            const int qq = q0 + j0 + j, tap = p.fd_cb.div(qq), cb = qq - tap * p.cin_blocks;
+            const int r = p.fd_s.div(tap), s = tap - r * p.S;
             if constexpr (cta2)
               tma_load_4d_2sm_a(&tmX, fb, sa + box_bytes * (2u + j), cb * 64, w0 + s - p.pad, h0 + r - p.pad, n0);
             else
@@ -751,7 +752,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
     if (rank == 0)
     for (int t = u0; t < total; t += ustep, ++it) {
       const int buf = it & 1; const uint32_t use = (uint32_t)(it >> 1);
-      const int split = t / tiles_per_split;
+      const int split = p.fd_tps.div(t);
       const int b_begin = split * p.boxes_per_split;
       int b_end = b_begin + p.boxes_per_split; if (b_end > p.boxes_total) b_end = p.boxes_total;
       mbar_wait_a(tempty0 + 8u * buf, (use & 1) ^ 1);
@@ -785,8 +786,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
     int it = 0;
     for (int t = u0; t < total; t += ustep, ++it) {
       const int buf = it & 1; const uint32_t use = (uint32_t)(it >> 1);
-      const int rem = t % tiles_per_split;
-      const int m = (cta2 ? 2 : 1) * (rem / p.q_tiles) + (int)rank, q0 = (rem % p.q_tiles) * p.nb;
+      const int rem = t - p.fd_tps.div(t) * tiles_per_split, mq = p.fd_qt.div(rem);
+      const int m = (cta2 ? 2 : 1) * mq + (int)rank, q0 = (rem - mq * p.q_tiles) * p.nb;
       const int row = m * 128 + q * 32 + lane;
       const bool valid = row < p.cout;
       mbar_wait(&tfull_bar[buf], use & 1);
@@ -882,6 +883,9 @@ int conv_wgrad(const Act& x, const Act& dy, int R, int S, int pad, float* dw, in
   p.boxes_per_split = (p.boxes_total + splits - 1) / splits;
   p.splits = (p.boxes_total + p.boxes_per_split - 1) / p.boxes_per_split;
   p.cout = dy.C; p.ldw = R * S * x.C; p.dw = dw;
+  p.fd_tps = FastDiv::make(tiles); p.fd_qt = FastDiv::make(p.q_tiles);
+  p.fd_tw = FastDiv::make(p.tiles_w); p.fd_twh = FastDiv::make(p.tiles_w * p.tiles_h);
+  p.fd_cb = FastDiv::make(p.cin_blocks); p.fd_s = FastDiv::make(S);
   const int stage_bytes = colbox ? 2 * p.kp * 128 + 18432 : p.kp * 128 * (2 + (cta2 ? p.nb / 2 : p.nb));
   p.stages = kSmemBudget / stage_bytes;
   if (p.stages > kMaxStages) p.stages = kMaxStages;
