@@ -48,15 +48,15 @@ def traffic_from_profile(variant, B):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 50 ms while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms.  Started before the warm-up (nvidia-smi needs a few
+    hundred ms to produce its first row on an 8-GPU box); only rows stamped inside the timed region (`with` block,
+    + one period) are summarised."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
-        self.idx, self.rows, self.proc = gpu_index, [], None
-
-    def __enter__(self):
+        self.idx, self.rows, self.proc, self.t0, self.t1 = gpu_index, [], None, None, None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE,
@@ -65,23 +65,28 @@ class ClockSampler:
             self.t.start()
         except Exception:
             self.proc = None
-        return self
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def __enter__(self):
+        self.t0 = time.time()
+        return self
 
     def __exit__(self, *a):
+        self.t1 = time.time()
         if self.proc:
-            time.sleep(0.25)
+            time.sleep(0.12)
             self.proc.terminate()
             self.t.join(timeout=2)
 
     def summary(self):
-        sm, mx, reasons = [], 0, set()
-        for r in self.rows:
+        inside = [r for t, r in self.rows if self.t0 is not None and self.t0 <= t <= self.t1 + 0.06]
+        sm, mx, pw, reasons = [], 0, [], set()
+        for r in inside:
             try:
-                sm.append(float(r[1])); mx = max(mx, float(r[2]))
+                sm.append(float(r[1])); mx = max(mx, float(r[2])); pw.append(float(r[3]))
             except Exception:
                 continue
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
@@ -89,7 +94,7 @@ class ClockSampler:
                     reasons.add(name)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "power_w_max": max(pw) if pw else None}
 
 
 def synth(variant, B, rank, steps):
@@ -235,6 +240,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    clk = ClockSampler(local_rank)  # started now: its first rows arrive during the warm-up
     # ---- kernel launches per step (eager step 0 also does the one-time initialisation)
     l0 = tr.eng.launch_count()
     step(dev_batches[0])
@@ -244,7 +250,7 @@ def main():
     # ---- timed: device-resident inputs
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local_rank) as clk:
+    with clk:
         e0.record()
         for i in range(args.steps):
             loss_t = step(dev_batches[i % nb])
