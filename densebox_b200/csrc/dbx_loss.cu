@@ -16,7 +16,7 @@
 
 namespace dbx {
 
-static constexpr int MAPW = 60, MAPN = 3600, LT = 256;
+static constexpr int MAPW = 60, MAPN = 3600, LT = 1024;  // one CTA of 32 warps per sample: the kernel is latency-bound
 
 
 struct Box { int x0, x1, y0, y1; };  // python slice bounds, already clipped: [x0,x1) x [y0,y1)
@@ -60,11 +60,42 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
   return s;
 }
 
+// Exclusive prefix sum of one int per thread over the block (LT threads); `ws` = LT/32 ints of shared memory.
+// Returns the exclusive prefix of this thread; *total = sum over the block.
+__device__ __forceinline__ int block_exscan(int v, int* ws, int* total) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  __syncthreads();
+  if (lane == 31) ws[w] = inc;
+  __syncthreads();
+  if (w == 0) {
+    int x = lane < LT / 32 ? ws[lane] : 0, y = x;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, y, o);
+      if (lane >= o) y += t;
+    }
+    if (lane < LT / 32) ws[lane] = y - x;  // exclusive warp offsets
+    if (lane == 31) ws[LT / 32] = y;        // block total
+  }
+  __syncthreads();
+  *total = ws[LT / 32];
+  return ws[w] + inc - v;
+}
+
 // Mark the k largest keys (ties at the threshold: lowest index first) by setting sel[i] = 1. keys are the bit
-// patterns of non-negative floats (order preserving).  All LT threads call this.
+// patterns of non-negative floats (order preserving).  All LT threads call this.  4-pass radix select on 8-bit
+// digits: histogram with shared-memory atomics, then the digit of the k-th largest key is found by a block-wide
+// suffix count (thread d < 256 owns digit d), no serial loops.
 __device__ void topk_mark(const uint32_t* keys, int k, unsigned char* sel, uint32_t* hist, int* sc) {
   if (k <= 0) return;
   if (k > MAPN) k = MAPN;
+  int* ws = sc + 4;  // LT/32 + 1 ints of scan workspace behind the two result slots
   uint32_t prefix = 0, pmask = 0;
   int remaining = k;
   for (int shift = 24; shift >= 0; shift -= 8) {
@@ -75,14 +106,12 @@ __device__ void topk_mark(const uint32_t* keys, int k, unsigned char* sel, uint3
       if ((key & pmask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-      int acc = 0, bin = 255;
-      for (; bin > 0; --bin) {
-        if (acc + (int)hist[bin] >= remaining) break;
-        acc += (int)hist[bin];
-      }
-      sc[0] = bin; sc[1] = remaining - acc;
-    }
+    // thread t < 256 takes digit d = 255 - t: its exclusive prefix = number of keys with a LARGER digit
+    const int mine = threadIdx.x < 256 ? (int)hist[255 - threadIdx.x] : 0;
+    int total;
+    const int above = block_exscan(mine, ws, &total);
+    if (threadIdx.x < 256 && above < remaining && above + mine >= remaining) { sc[0] = 255 - (int)threadIdx.x; sc[1] = remaining - above; }
+    if (threadIdx.x == 0 && total < remaining) { sc[0] = 0; sc[1] = remaining - (total - (int)hist[0]); }  // cannot happen (k <= MAPN)
     __syncthreads();
     prefix |= (uint32_t)sc[0] << shift;
     pmask |= 255u << shift;
@@ -94,15 +123,8 @@ __device__ void topk_mark(const uint32_t* keys, int k, unsigned char* sel, uint3
   const int b0 = threadIdx.x * per, b1 = min(b0 + per, MAPN);
   int cnt = 0;
   for (int i = b0; i < b1; ++i) cnt += keys[i] == prefix;
-  int* scan = reinterpret_cast<int*>(hist);
-  scan[threadIdx.x] = cnt;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    int run = 0;
-    for (int t = 0; t < LT; ++t) { const int c = scan[t]; scan[t] = run; run += c; }
-  }
-  __syncthreads();
-  int rank = scan[threadIdx.x];
+  int total;
+  int rank = block_exscan(cnt, ws, &total);
   for (int i = b0; i < b1; ++i) {
     const uint32_t key = keys[i];
     if (key > prefix) sel[i] = 1;
@@ -117,7 +139,7 @@ __global__ void __launch_bounds__(LT) loss_kernel(const LossParams p) {
   __shared__ unsigned char lmm[4][MAPN];
   __shared__ uint32_t hist[256];
   __shared__ double red[LT / 32];
-  __shared__ int sc[4];
+  __shared__ int sc[4 + LT / 32 + 1];
   __shared__ int lmx[4], lmy[4];
 
   const int b = blockIdx.x, tid = threadIdx.x;
