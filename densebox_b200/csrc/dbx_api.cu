@@ -75,7 +75,7 @@ int dbx_dropout_mask(void* mask, unsigned long long n, unsigned long long seed, 
 }
 
 int dbx_im2col3x3_c3(const float* x, void* out, int N, int H, int W, void* stream) {
-  return im2col3x3_c3(x, out, N, H, W, 1, (cudaStream_t)stream);
+  return im2col3x3_c3(x, out, N, H, W, 1, (cudaStream_t)stream);  // 64-channel layout, zero channels written
 }
 int dbx_maxpool2x2_fwd(const void* y, int N, int H, int W, int C, int y_cs, int y_coff, void* out, int o_cs, int o_coff,
                        void* stream) {

@@ -28,8 +28,12 @@ __device__ __forceinline__ void fold_bias_partials(const float* acc, int cc, flo
 // ------------------------------------------------------------------------------------------------ ingest
 // X fp32 NCHW [N,3,H,W] -> bf16 [N,H,W,64]: channel (r*3+s)*3+c holds X[n,c,y+r-1,x+s-1] (zero outside), channels
 // 27..63 are zero.  conv1_1 (DenseBox.py:185) then is a K=64 1x1 GEMM on the tensor cores.
+// mode 0 / 1: 64 channels per pixel (1: also write the zero channels 32..63).
+// mode 2 ("pairs"): 32 channels per pixel, so one 128-byte GEMM row holds the taps of TWO horizontally adjacent
+// pixels, and channel 27 is the constant 1 (its weight column is zero; in the weight gradient it collects the bias
+// gradient).  Half the bytes of the 64-channel layout — this tensor is pure HBM traffic.
 __global__ void im2col3x3_c3_kernel(const float* __restrict__ x, bf16* __restrict__ out, int N, int H, int W,
-                                    int write_pad) {
+                                    int mode) {
   const size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (pix >= (size_t)N * H * W) return;
   const int xw = (int)(pix % W), y = (int)((pix / W) % H), n = (int)(pix / ((size_t)W * H));
@@ -49,20 +53,41 @@ __global__ void im2col3x3_c3_kernel(const float* __restrict__ x, bf16* __restric
       for (int c = 0; c < 3; ++c) f[(r * 3 + s) * 3 + c] = ok ? __ldg(xn + ((size_t)c * H + yy) * W + xx) : 0.f;
     }
   }
-  uint4* o = reinterpret_cast<uint4*>(out + pix * 64);
+  if (mode == 2) f[27] = 1.f;
+  uint4* o = reinterpret_cast<uint4*>(out + pix * (mode == 2 ? 32 : 64));
 #pragma unroll
   for (int q = 0; q < 4; ++q) o[q] = pack8(f + 8 * q);
-  if (write_pad) {
+  if (mode == 1) {
 #pragma unroll
     for (int q = 4; q < 8; ++q) o[q] = make_uint4(0u, 0u, 0u, 0u);
   }
 }
 
-// write_pad = 0: channels 32..63 are left untouched (the engine zeroes them once at creation).
-int im2col3x3_c3(const float* x, void* out, int N, int H, int W, int write_pad, cudaStream_t st) {
-  if (!x || !out) return DBX_ERR_ARG;
+// mode 0: channels 32..63 are left untouched (the engine zeroes them once at creation); 1: written; 2: pairs layout.
+int im2col3x3_c3(const float* x, void* out, int N, int H, int W, int mode, cudaStream_t st) {
+  if (!x || !out || mode < 0 || mode > 2 || (mode == 2 && (W & 1))) return DBX_ERR_ARG;
   const size_t total = (size_t)N * H * W;
-  im2col3x3_c3_kernel<<<grid_for(total, 128), 128, 0, st>>>(x, (bf16*)out, N, H, W, write_pad);
+  im2col3x3_c3_kernel<<<grid_for(total, 128), 128, 0, st>>>(x, (bf16*)out, N, H, W, mode);
+  return (int)cudaGetLastError();
+}
+
+// conv1_1 in the pairs layout is a 128 x 64 GEMM matrix [[W 0] [0 W]] (rows 0..63: even pixels, taps in columns
+// 0..31; rows 64..127: odd pixels, columns 32..63).  Its weight gradient arrives in `scratch` [128][64] with the two
+// diagonal blocks holding the even- and odd-pixel halves of dW, the bias gradient in column 27 of each block (the
+// constant-1 tap) and cross terms in the off-diagonal blocks.  Fold: gw[both blocks][c][k] += even + odd (k != 27),
+// gb[c] = gb[64 + c] += even + odd of column 27; the off-diagonal blocks and column 27 of gw receive nothing, so the
+// two copies stay identical and the zero columns stay zero under SGD.
+__global__ void conv1_1_fold_pairs_kernel(const float* __restrict__ scratch, float* __restrict__ gw,
+                                          float* __restrict__ gb) {
+  const int c = blockIdx.x, k = threadIdx.x;  // 64 blocks x 32 threads
+  const float s = scratch[c * 64 + k] + scratch[(64 + c) * 64 + 32 + k];
+  if (k == 27) { gb[c] += s; gb[64 + c] += s; }
+  else { gw[c * 64 + k] += s; gw[(64 + c) * 64 + 32 + k] += s; }
+}
+
+int conv1_1_fold_pairs(const float* scratch, float* gw, float* gb, cudaStream_t st) {
+  if (!scratch || !gw || !gb) return DBX_ERR_ARG;
+  conv1_1_fold_pairs_kernel<<<64, 32, 0, st>>>(scratch, gw, gb);
   return (int)cudaGetLastError();
 }
 

@@ -3,7 +3,7 @@
 // the hand-written backward (the autograd graph of DenseBox.py:2925), plus the fused SGD step (:2926).
 //
 // HBM layout (all activations NHWC bf16, 64-byte aligned regions carved from the workspace):
-//   col0[N,H,W,64] -> a11,a12[N,H,W,64] -> p1 -> a21,a22[.,128] -> p2 -> a31,a32[.,256]
+//   col0[N,H,W/2,64] (27 taps + constant 1 of two adjacent pixels per row) -> a11,a12[N,H,W,64] -> p1 -> a21,a22[.,128] -> p2 -> a31,a32[.,256]
 //   fusion[N,H/4,W/4,768] = [ upsample(conv4_4) : 512 | conv3_4 : 256 ]   (torch.cat is free: producers write here)
 //   p3 -> a41..a44[.,512];  hd[N,H/4,W/4,512*heads] (post-dropout), head_out fp32 [N,H/4,W/4,16|32]
 //   refine: rp[.,H/8,W/8,64] -> r1 -> r2 -> rup[N,H/4,W/4,64] -> rf_out fp32 [.,16]
@@ -41,6 +41,11 @@ struct Buf { std::string name; size_t off, bytes; };
 
 struct Net {
   int variant, N, H, W, train;
+  // conv1_1 "pairs" layout (default): col0 holds 32 channels per pixel, i.e. one 128-byte GEMM row = two adjacent
+  // pixels; conv1_1 is the 128 x 64 matrix [[W 0] [0 W]] producing a11 viewed as [N,H,W/2,128].  Halves the HBM
+  // traffic of col0 (im2col write, conv1_1 read, wgrad read) and the constant-1 tap yields the bias gradient inside
+  // the weight gradient.  DBX_CONV1_PAIRS=0 at creation: the 64-channel layout (A/B, parity reference).
+  bool pairs = true;
   int nh, HC;            // heads, head_out channels
   int ch_start[5];       // rows of conv5_2 group owned by head h
   std::vector<Group> groups;
@@ -116,12 +121,13 @@ struct Net {
 
   void build(int variant_, int N_, int H_, int W_, int train_) {
     variant = variant_; N = N_; H = H_; W = W_; train = train_;
+    { const char* e = getenv("DBX_CONV1_PAIRS"); pairs = !(e && e[0] == '0') && (W % 2 == 0); }
     nh = variant == 0 ? 2 : (variant == 1 ? 3 : 4);
     HC = variant == 2 ? 32 : 16;
     const int starts[5] = {0, 1, 5, 9, 17};
     for (int i = 0; i < 5; ++i) ch_start[i] = starts[i];
     // ---- GEMM groups
-    add_group("conv1_1", 64, 1, 64, false);
+    add_group("conv1_1", pairs ? 128 : 64, 1, 64, false);
     add_group("conv1_2", 64, 9, 64, true);
     add_group("conv2_1", 128, 9, 64, true);
     add_group("conv2_2", 128, 9, 128, true);
@@ -177,7 +183,7 @@ struct Net {
     add_buf("rng", 256);      // {seed, offset} (2 x u64) of the in-epilogue dropout draw
     add_buf("scalars", 256);  // [0] loss f32, [1] counter u32, [2..3] info i32, [16..] loss_partial
     add_buf("loss_partial", (size_t)N * 4);
-    add_buf("col0", px1 * 64 * 2);
+    add_buf("col0", px1 * (pairs ? 32 : 64) * 2);
     add_buf("a11", px1 * 64 * 2); add_buf("a12", px1 * 64 * 2); add_buf("p1", px2 * 64 * 2);
     add_buf("a21", px2 * 128 * 2); add_buf("a22", px2 * 128 * 2); add_buf("p2", px4 * 128 * 2);
     add_buf("a31", px4 * 256 * 2); add_buf("a32", px4 * 256 * 2); add_buf("fusion", px4 * 768 * 2);
@@ -196,6 +202,7 @@ struct Net {
     }
     if (train) {
       add_buf("g32", flat_n * 4);
+      add_buf("g11p", 128 * 64 * 4);  // conv1_1 weight gradient of one backward pass in the pairs layout, before the fold
       add_buf("v32", flat_n * 4);
       add_buf("drop", px4 * 512 * nh * 2);
       add_buf("pi1", px2 * 8 * 2);    // arg-max maps of pool1 / pool2: u16 per (pooled pixel, 8-channel vector)
@@ -240,13 +247,20 @@ struct Net {
     if (id < 0 || !src) return DBX_ERR_ARG;
     const Param& p = params[id];
     const Group& g = groups[p.grp];
+    const bool dup = pairs && std::string(name) == "conv1_1";  // second diagonal block: rows 64.., columns 32..
     if (is_bias) {
       cudaError_t e = cudaMemcpy2DAsync(W32() + g.b_off + p.rowK, 4, src, (size_t)s_co * 4, 4, p.cout,
                                         cudaMemcpyDeviceToDevice, st);
+      if (e == cudaSuccess && dup)
+        e = cudaMemcpy2DAsync(W32() + g.b_off + 64, 4, src, (size_t)s_co * 4, 4, p.cout, cudaMemcpyDeviceToDevice, st);
       return (int)e;
     }
-    return pack_weights(src, p.cout, p.cin, p.R, p.S, s_co, s_ci, s_r, s_s, WK() + g.w_off, g.ld, p.rowK, p.kK,
-                        p.cin_pad, nullptr, 0, 0, 0, 0, W32() + g.w_off, st);
+    int rc = pack_weights(src, p.cout, p.cin, p.R, p.S, s_co, s_ci, s_r, s_s, WK() + g.w_off, g.ld, p.rowK, p.kK,
+                          p.cin_pad, nullptr, 0, 0, 0, 0, W32() + g.w_off, st);
+    if (!rc && dup)
+      rc = pack_weights(src, p.cout, p.cin, p.R, p.S, s_co, s_ci, s_r, s_s, WK() + g.w_off, g.ld, 64, 32, p.cin_pad,
+                        nullptr, 0, 0, 0, 0, W32() + g.w_off, st);
+    return rc;
   }
   int get_tensor(const char* name, int is_bias, int which, float* dst, long s_co, long s_ci, long s_r, long s_s,
                  cudaStream_t st) {
@@ -353,8 +367,15 @@ struct Net {
       DBX_TRY((int)cudaEventRecord(ev_join, side));
       dgrad_pending = true;
     }
-    DBX_K("im2col", 0.0, im2col3x3_c3(x, col0.ptr, N, H, W, 0, st));
-    DBX_TRY(conv(col0, "conv1_1", 1, 0, a11, true, nullptr, 0, 0, false, 0, st));
+    DBX_K("im2col", 0.0, im2col3x3_c3(x, col0.ptr, N, H, W, pairs ? 2 : 0, st));
+    if (pairs) {
+      Act col0p = act("col0", H, W / 2, 64), a11p = act("a11", H, W / 2, 128);
+      ConvEpilogue e;
+      e.bias = bias_of("conv1_1"); e.relu = 1;
+      DBX_K("fprop:conv1_1", 2.0 * pixels(a11) * macs_of("conv1_1"), conv_fprop(col0p, wk_of("conv1_1"), 1, 1, 0, a11p, e, 0, st));
+    } else {
+      DBX_TRY(conv(col0, "conv1_1", 1, 0, a11, true, nullptr, 0, 0, false, 0, st));
+    }
     DBX_TRY(conv(a11, "conv1_2", 3, 1, a12, true, nullptr, 0, 0, false, 0, st));
     DBX_K("pool_fwd", 0.0, maxpool2x2_fwd(a12, p1, st, train ? buf("pi1") : nullptr));
     DBX_TRY(conv(p1, "conv2_1", 3, 1, a21, true, nullptr, 0, 0, false, 0, st));
@@ -533,8 +554,29 @@ struct Net {
     if (pool_idx) DBX_K("pool_bwd", 0.0, maxpool2x2_bwd_idx(p1, d_p1, buf("pi1"), d_a12, st, fuse ? gb_of("conv1_2") : nullptr));
     else DBX_K("pool_bwd", 0.0, maxpool2x2_bwd(a12, d_p1, nullptr, d_a12, st, fuse ? gb_of("conv1_2") : nullptr));
     DBX_TRY(wgrad(a11, d_a12, "conv1_2", 3, 1, st, fuse));
-    DBX_TRY(dgrad(d_a12, "conv1_2", 3, 1, d_a11, &a11, st, fuse_short ? "conv1_1" : nullptr));
-    DBX_TRY(wgrad(col0, d_a11, "conv1_1", 1, 0, st, fuse_short));
+    DBX_TRY(dgrad(d_a12, "conv1_2", 3, 1, d_a11, &a11, st, (fuse_short && !pairs) ? "conv1_1" : nullptr));
+    if (pairs) {
+      // weight + bias gradient of conv1_1 in the pairs layout: one wgrad into a scratch matrix, then the fold
+      Act col0p = act("col0", H, W / 2, 64), d_a11p = act("d_a11", H, W / 2, 128);
+      float* scratch = (float*)buf("g11p");
+      cudaStream_t ws = (side && !profiling) ? side : st;
+      if (ws == side) {
+        DBX_TRY((int)cudaEventRecord(ev_fork, st));
+        DBX_TRY((int)cudaStreamWaitEvent(side, ev_fork, 0));
+        side_used = true;
+      }
+      DBX_TRY((int)cudaMemsetAsync(scratch, 0, 128 * 64 * 4, ws));
+      if (ws == side) {
+        launches += 2;
+        DBX_TRY(conv_wgrad(col0p, d_a11p, 1, 1, 0, scratch, 0, ws));
+        DBX_TRY(conv1_1_fold_pairs(scratch, gw_of("conv1_1"), gb_of("conv1_1"), ws));
+      } else {
+        DBX_K("wgrad:conv1_1", 2.0 * pixels(d_a11) * macs_of("conv1_1"), conv_wgrad(col0p, d_a11p, 1, 1, 0, scratch, 0, ws));
+        DBX_K("fold:conv1_1", 0.0, conv1_1_fold_pairs(scratch, gw_of("conv1_1"), gb_of("conv1_1"), ws));
+      }
+    } else {
+      DBX_TRY(wgrad(col0, d_a11, "conv1_1", 1, 0, st, fuse_short));
+    }
     return join_side(st);
   }
 

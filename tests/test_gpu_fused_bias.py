@@ -88,3 +88,40 @@ def test_heads2_dgrad_kernel_matches_tensor_core_path():
         assert d <= 2e-3 or n.startswith(("conv1", "conv2")), (n, d)  # early layers: chaotic ReLU routing
     for n in ("conv5_1_det.weight", "conv5_1_det.bias", "conv5_1_loc.bias", "conv5_1_landmark.weight"):
         assert n in ref
+
+
+def _all_grads(pairs):
+    from densebox_b200 import densebox_loss
+    os.environ["DBX_CONV1_PAIRS"] = "1" if pairs else "0"   # read when the engine is created
+    try:
+        _, net = build("densebox")
+        net = net.cuda().eval()
+        x, lab, rand, _ = make_inputs(3, "densebox")
+        score, loc = net(x.cuda())
+        L = densebox_loss(score, loc, lab["bbox"], rand_neg_idx=rand)
+        L.backward()
+        torch.cuda.synchronize()
+        g = {n: p.grad.detach().float().cpu() for n, p in net.named_parameters() if p.grad is not None}
+        return g, float(L.detach()), score.detach().cpu(), {n: p.detach().float().cpu() for n, p in net.named_parameters()}
+    finally:
+        os.environ.pop("DBX_CONV1_PAIRS", None)
+
+
+def test_conv1_1_pairs_layout_matches_64_channel_layout():
+    """conv1_1 as the 128 x 64 matrix [[W 0] [0 W]] over rows of two pixels (default) vs the plain 64-channel im2col
+    layout: the forward pass must be bit-identical (same products, zeros elsewhere), hence every other gradient too;
+    the conv1_1 weight / bias gradients (one wgrad + fold, bias from the constant-1 tap) differ by fp32 summation
+    order only: 1e-4 of the largest entry."""
+    g0, L0, s0, w0 = _all_grads(pairs=False)
+    g1, L1, s1, w1 = _all_grads(pairs=True)
+    assert torch.equal(s0, s1) and L0 == L1
+    for n in w0:
+        assert torch.equal(w0[n], w1[n]), n                       # parameters round-trip through both layouts
+    assert set(g0) == set(g1)
+    for n in g0:
+        scale = g0[n].abs().max().item()
+        err = (g1[n] - g0[n]).abs().max().item() / (scale + 1e-30)
+        if n.startswith(("conv1_1", "conv1_1_1")):
+            assert scale > 0 and err <= 1e-4, (n, err)
+        else:
+            assert err <= 2e-5, (n, err)                          # red.add order in wgrad only
