@@ -95,6 +95,15 @@ int pack_weights(const float* src, int co, int ci, int R, int S, long s_co, long
 int unpack_weights(const float* srcK, long ldK, long rowK, long kK, int cin_pad, float* dst, int co, int ci, int R,
                    int S, long s_co, long s_ci, long s_r, long s_s, cudaStream_t st);
 int transpose_dgrad(const void* wk, void* wd, int rows, int T, int cin_pad, int kpad, cudaStream_t st);
+// the same for up to 16 weight matrices in one launch (element offsets into the flat bf16 buffers)
+struct TransposeBatch {
+  static constexpr int kMax = 16;
+  struct G { long long wk_off, wd_off; int rows, T, cin_pad, kpad, block0; };
+  G g[kMax];
+  int n;
+};
+int transpose_dgrad_multi(const void* wk_base, void* wd_base, const TransposeBatch& tb, int total_blocks,
+                          cudaStream_t st);
 int sgd_step(float* w, float* g, float* v, void* wb, size_t n, float lr, float momentum, float wd, int first,
              int zero_grad, cudaStream_t st);
 int cast_bf16(const float* src, void* dst, size_t n, cudaStream_t st);

@@ -667,6 +667,41 @@ __global__ void transpose_dgrad_kernel(const bf16* __restrict__ wk, bf16* __rest
   }
 }
 
+// All groups of a network in ONE launch: block -> (group, 32 x 32 tile, tap) through a small table passed by value.
+__global__ void transpose_dgrad_multi_kernel(const bf16* __restrict__ wk_base, bf16* __restrict__ wd_base,
+                                             const TransposeBatch tb) {
+  __shared__ bf16 tile[32][34];
+  int gi = 0;
+#pragma unroll 1
+  while (gi + 1 < tb.n && (int)blockIdx.x >= tb.g[gi + 1].block0) ++gi;
+  const TransposeBatch::G g = tb.g[gi];
+  int local = (int)blockIdx.x - g.block0;
+  const int tiles_i = (g.cin_pad + 31) / 32, tiles_o = (g.rows + 31) / 32;
+  const int t = local / (tiles_i * tiles_o);
+  local -= t * tiles_i * tiles_o;
+  const int o0 = (local / tiles_i) * 32, i0 = (local % tiles_i) * 32;
+  const bf16* wk = wk_base + g.wk_off;
+  bf16* wd = wd_base + g.wd_off;
+  const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+  for (int k = ty; k < 32; k += 8) {
+    const int o = o0 + k, i = i0 + tx;
+    tile[k][tx] = (o < g.rows && i < g.cin_pad) ? wk[((size_t)o * g.T + t) * g.cin_pad + i] : __float2bfloat16_rn(0.f);
+  }
+  __syncthreads();
+  const int tf = g.T - 1 - t;
+  for (int k = ty; k < 32; k += 8) {
+    const int i = i0 + k, o = o0 + tx;
+    if (i < g.cin_pad && o < g.rows) wd[((size_t)i * g.T + tf) * g.kpad + o] = tile[tx][k];
+  }
+}
+
+int transpose_dgrad_multi(const void* wk_base, void* wd_base, const TransposeBatch& tb, int total_blocks,
+                          cudaStream_t st) {
+  if (!wk_base || !wd_base || tb.n < 1 || tb.n > TransposeBatch::kMax || total_blocks < 1) return DBX_ERR_ARG;
+  transpose_dgrad_multi_kernel<<<total_blocks, dim3(32, 8), 0, st>>>((const bf16*)wk_base, (bf16*)wd_base, tb);
+  return (int)cudaGetLastError();
+}
+
 int transpose_dgrad(const void* wk, void* wd, int rows, int T, int cin_pad, int kpad, cudaStream_t st) {
   if (!wk || !wd) return DBX_ERR_ARG;
   dim3 grid((cin_pad + 31) / 32, (rows + 31) / 32, T), block(32, 8);

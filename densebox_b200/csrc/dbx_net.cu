@@ -283,10 +283,17 @@ struct Net {
   bool dgrad_pending = false; // transposes in flight on the side stream
   int refresh_dgrad(cudaStream_t st) {
     dgrad_stale = false;
+    TransposeBatch tb{};
+    int blocks = 0;
     for (auto& g : groups) {
       if (!g.need_dgrad) continue;
-      DBX_K("transpose_dgrad", 0.0, transpose_dgrad(WK() + g.w_off, WD() + g.wd_off, g.rows, g.T, g.cin_pad, g.kpad, st));
+      if (tb.n == TransposeBatch::kMax) return DBX_ERR_ARG;
+      TransposeBatch::G& e = tb.g[tb.n++];
+      e.wk_off = (long long)g.w_off; e.wd_off = (long long)g.wd_off;
+      e.rows = g.rows; e.T = g.T; e.cin_pad = g.cin_pad; e.kpad = g.kpad; e.block0 = blocks;
+      blocks += ((g.cin_pad + 31) / 32) * ((g.rows + 31) / 32) * g.T;
     }
+    DBX_K("transpose_dgrad", 0.0, transpose_dgrad_multi(WK(), WD(), tb, blocks, st));  // every filter in one launch
     return DBX_OK;
   }
 
