@@ -125,7 +125,6 @@ struct FpropParams {
   FastDiv fd_nt, fd_tw, fd_twh;   // division by n_tiles, tiles_w, tiles_w * tiles_h
   int cout;
   float* colsum; int csum_off;  // fused bias gradient: global fp32 [cout], smem offset of the per-CTA partial sums
-  int debug;               // measurement only (DBX_DEBUG): 1 = no TMA loads, 2 = no MMAs — results are garbage
   int stages, kps;         // pipeline stages; K blocks (64 channels of one tap) per stage
   uint32_t idesc, tmem_cols;
   const float* bias;
@@ -211,12 +210,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint32_t tfull0 = smem_u32(&tfull_bar[0]), tempty0 = smem_u32(&tempty_bar[0]);
   // opaque to the optimiser: otherwise ptxas re-derives every window address inside the hot loops
   // (S2R SR_CgaCtaId + LEA per barrier access, ~30 cycles of latency each on a single-warp issue loop)
-#ifndef DBX_OPAQUE
-#define DBX_OPAQUE 1
-#endif
-#if DBX_OPAQUE
   asm volatile("" : "+r"(smem_base), "+r"(full0), "+r"(empty0), "+r"(tfull0), "+r"(tempty0));
-#endif
 
   if (warp == 0) {
     // ===================== TMA producer (whole warp walks the schedule, one elected lane issues) ===============
@@ -234,9 +228,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               const uint32_t fb = full0 + 8u * stage;
               const uint32_t sa = smem_base + (uint32_t)stage * stage_bytes;
               const int kc = sx * p.cin + cb * 64;              // filter column of tap (r = 0, s): + 3 * cin per row
-              if (p.debug & 1) {
-                if (rank == 0) mbar_arrive_expect_tx_a(fb, 0u);
-              } else if constexpr (cta2) {
+              if constexpr (cta2) {
                 if (rank == 0) mbar_arrive_expect_tx_a(fb, 2u * slot_bytes);
                 tma_load_4d_2sm_a(&tmA, fb, sa, cb * 64, w0 + sx, h0, n0);
 #pragma unroll
@@ -262,10 +254,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (elect_one_sync()) {
           const uint32_t fb = full0 + 8u * stage;
           uint32_t sa = smem_base + (uint32_t)stage * stage_bytes;
-          if (p.debug & 1) {
-            if (rank == 0) mbar_arrive_expect_tx_a(fb, 0u);
-            nk = 0;
-          } else if constexpr (cta2) {
+          if constexpr (cta2) {
             // both CTAs' bytes land on the leader's barrier; only the leader arms it
             if (rank == 0) mbar_arrive_expect_tx_a(fb, 2u * (uint32_t)nk * (a_bytes + b_bytes));
           } else {
@@ -314,19 +303,17 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               const uint32_t a_lo = (smem_base + (uint32_t)stage * stage_bytes) >> 4;
               const uint64_t da0 = desc_hi | (uint64_t)a_lo, db0 = desc_hi | (uint64_t)(a_lo + (kColBox >> 4));
               const uint32_t bt = b_bytes >> 4;
-              if (!(p.debug & 2)) {
 #pragma unroll
-                for (int r = 0; r < 3; ++r)
+              for (int r = 0; r < 3; ++r)
 #pragma unroll
-                  for (int k = 0; k < 4; ++k) {  // filter row r: the box shifted by r image rows = r atoms (64 x 16 B)
-                    if constexpr (cta2)
-                      umma_bf16_2sm(d_tmem, da0 + 64 * r + 2 * k, db0 + (uint64_t)r * bt + 2 * k, p.idesc,
-                                    (uint32_t)((st | r | k) != 0));
-                    else
-                      umma_bf16(d_tmem, da0 + 64 * r + 2 * k, db0 + (uint64_t)r * bt + 2 * k, p.idesc,
-                                (uint32_t)((st | r | k) != 0));
-                  }
-              }
+                for (int k = 0; k < 4; ++k) {  // filter row r: the box shifted by r image rows = r atoms (64 x 16 B)
+                  if constexpr (cta2)
+                    umma_bf16_2sm(d_tmem, da0 + 64 * r + 2 * k, db0 + (uint64_t)r * bt + 2 * k, p.idesc,
+                                  (uint32_t)((st | r | k) != 0));
+                  else
+                    umma_bf16(d_tmem, da0 + 64 * r + 2 * k, db0 + (uint64_t)r * bt + 2 * k, p.idesc,
+                              (uint32_t)((st | r | k) != 0));
+                }
               if constexpr (cta2) umma_commit_2sm_a(empty0 + 8u * stage, 3); else umma_commit_a(empty0 + 8u * stage);
             }
             __syncwarp();
@@ -341,7 +328,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             uint32_t a_lo = (smem_base + (uint32_t)stage * stage_bytes) >> 4;
 #pragma unroll
             for (int j = 0; j < kps; ++j, a_lo += slot_bytes >> 4) {
-              if (j >= nk || (p.debug & 2)) break;
+              if (j >= nk) break;
               const uint64_t da = desc_hi | (uint64_t)a_lo, db = desc_hi | (uint64_t)(a_lo + 1024u);  // B at +16 KB
 #pragma unroll
               for (int k = 0; k < 4; ++k) {  // +32 B (2 x 16 B units) per UMMA_K = 16
@@ -556,7 +543,7 @@ int conv_fprop(const Act& x, const void* wk, int R, int S, int pad, const Act& o
   p.cta2 = cta2;
   const int slot_bytes = colbox ? 18432 + 3 * (cta2 ? block_n / 2 : block_n) * 128
                                 : 16384 + (cta2 ? block_n / 2 : block_n) * 128;
-  // K blocks per stage: a barrier round trip of the single-warp issue loops costs ~250 ns (tools/bench_debug.py:
+  // K blocks per stage: a barrier round trip of the single-warp issue loops costs ~250 ns (measured:
   // conv2_2 with neither TMA nor MMA still takes 0.113 ms of 0.152), which a 64-wide tile (128 cycles of MMA per K
   // block) cannot hide -> batch K blocks behind one barrier
   const int b_rows_cta = cta2 ? block_n / 2 : block_n;
@@ -592,7 +579,6 @@ int conv_fprop(const Act& x, const void* wk, int R, int S, int pad, const Act& o
   }
   p.idesc = umma_idesc_bf16(cta2 ? 256 : 128, block_n, 0, 0);
   p.tmem_cols = tmem_cols_for(2 * block_n);
-  { const char* e = getenv("DBX_DEBUG"); p.debug = e ? atoi(e) : 0; }
   p.bias = epi.bias; p.relu = epi.relu;
   p.aux = (const bf16*)epi.aux; p.aux_cs = epi.aux_cs; p.aux_coff = epi.aux_coff; p.aux_mode = epi.aux_mode;
   p.out = out.ptr; p.out_cs = out.cs; p.out_coff = out.coff; p.out_fp32 = epi.out_fp32;
