@@ -51,6 +51,12 @@ class DenseBoxTrainer:
         self._rng = self.eng.buffer("rng", torch.int64)
         drop_elems = self.eng.buffer("drop", torch.bfloat16).numel()
         self._rng_stride = (drop_elems + 127) // 128  # Philox calls consumed by one step
+        # prefetch(): host batch i+1 is copied on a side stream into staging buffers while step i computes
+        self._pf = None            # {"x": ..., "bbox": ..., ...} staging tensors (lazily allocated)
+        self._pf_key = None        # identity of the host tensors staged last
+        self._pf_stream = None
+        self._pf_ready = None      # event: staging complete (recorded on the copy stream)
+        self._pf_free = None       # event: staging buffers consumed (recorded on the compute stream)
         self.load_from_module()
 
     # ---- parameters
@@ -75,6 +81,51 @@ class DenseBoxTrainer:
             return
         src = torch.as_tensor(src)
         dst.copy_(src.reshape(dst.shape) if src.numel() == dst.numel() else src, non_blocking=True)
+
+    @staticmethod
+    def _key(*tensors):
+        return tuple((t.data_ptr(), tuple(t.shape)) if torch.is_tensor(t) else None for t in tensors)
+
+    def prefetch(self, x, bbox, vertices=None, labels=None, rand_neg_idx=None, lm_rand_neg_idx=None):
+        """Start the host->device copy of the NEXT batch (pinned host tensors) on a side stream; a following
+        `step()` called with the same tensors finds them in device staging buffers and only pays a device-to-device
+        copy.  The usual prefetching-loader pattern: `step(batch_i)`, `prefetch(batch_i+1)`, then read the loss."""
+        args = {"x": x, "bbox": bbox, "vertices": vertices, "labels": labels, "rand": rand_neg_idx,
+                "lm_rand": lm_rand_neg_idx}
+        if not all(v is None or (torch.is_tensor(v) and not v.is_cuda) for v in args.values()):
+            return  # device tensors or non-tensors: nothing to overlap, step() handles them
+        if self._pf is None:
+            self._pf = {"x": torch.empty_like(self.x), "bbox": torch.empty_like(self.bbox),
+                        "vertices": torch.empty_like(self.vertices), "labels": torch.empty_like(self.labels),
+                        "rand": torch.empty_like(self.rand), "lm_rand": torch.empty_like(self.lm_rand)}
+            self._pf_stream = torch.cuda.Stream(device=self.device)
+            self._pf_ready = torch.cuda.Event()
+            self._pf_free = torch.cuda.Event()
+            self._pf_free.record(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(self._pf_stream):
+            self._pf_stream.wait_event(self._pf_free)  # the previous staged batch has been consumed
+            for k, v in args.items():
+                if v is None:
+                    continue
+                dst = self._pf[k]
+                if k == "rand":
+                    dst[:, :v.shape[1]].copy_(v[:, :dst.shape[1]], non_blocking=True)
+                else:
+                    dst.copy_(v.reshape(dst.shape) if v.numel() == dst.numel() else v, non_blocking=True)
+            self._pf_ready.record(self._pf_stream)
+        self._pf_key = self._key(x, bbox, vertices, labels, rand_neg_idx, lm_rand_neg_idx)
+
+    def _take_prefetched(self, x, bbox, vertices, labels, rand_neg_idx, lm_rand_neg_idx):
+        """If exactly these host tensors were staged by prefetch(): substitute the staging buffers (device)."""
+        if self._pf_key is None or self._pf_key != self._key(x, bbox, vertices, labels, rand_neg_idx, lm_rand_neg_idx):
+            return x, bbox, vertices, labels, rand_neg_idx, lm_rand_neg_idx, False
+        self._pf_key = None
+        torch.cuda.current_stream(self.device).wait_event(self._pf_ready)
+        pf = self._pf
+        return (pf["x"], pf["bbox"], pf["vertices"] if vertices is not None else None,
+                pf["labels"] if labels is not None else None,
+                pf["rand"][:, :rand_neg_idx.shape[1]] if rand_neg_idx is not None else None,
+                pf["lm_rand"] if lm_rand_neg_idx is not None else None, True)
 
     def _fwd_loss_bwd(self):
         e = self.eng
@@ -127,6 +178,8 @@ class DenseBoxTrainer:
         """x [B,3,240,240] fp32 (host pinned or device), labels in 60-space. Returns the loss as a 0-dim CUDA tensor
         (this rank's shard; call .item() to read it back)."""
         e = self.eng
+        x, bbox, vertices, labels, rand_neg_idx, lm_rand_neg_idx, staged = self._take_prefetched(
+            x, bbox, vertices, labels, rand_neg_idx, lm_rand_neg_idx)
         self._stage(self.x, x)
         self._stage(self.bbox, bbox)
         self._stage(self.vertices, vertices)
@@ -143,6 +196,8 @@ class DenseBoxTrainer:
                 self.lm_rand.copy_(torch.randint(0, 3600, (self.B, 4), device=self.device))
             else:
                 self._stage(self.lm_rand, lm_rand_neg_idx)
+        if staged:  # the staging buffers may be refilled once these device-to-device copies are done
+            self._pf_free.record(torch.cuda.current_stream(self.device))
         if self.dropout:  # a fresh mask per step: advance the Philox counter offset (device side, graph safe)
             self._rng[0] = self.seed
             self._rng[1] = self.step_no * self._rng_stride

@@ -241,3 +241,29 @@ def test_inplace_philox_dropout_equals_explicit_mask():
     assert res[0][2] == res[1][2]
     # wgrad accumulates with fp32 atomics (order varies run to run): compare to accumulation noise
     assert (res[0][1] - res[1][1]).abs().max().item() <= 1e-4 * res[1][1].abs().max().item()
+
+
+def test_trainer_prefetch_matches_direct_step():
+    """trainer.prefetch(batch) + step(batch) (host->device copy on a side stream into staging buffers) must give the
+    same losses as step(batch) alone, over several steps with changing batches (staging-buffer reuse, events)."""
+    from densebox_b200 import DenseBoxTrainer
+    variant, B = "densebox", 2
+    batches = []
+    for s in range(4):
+        x, lab, rand, _ = make_inputs(B, variant, seed=20 + s)
+        batches.append((x.pin_memory(), torch.tensor(lab["bbox"]).pin_memory(), torch.tensor(rand).pin_memory()))
+    out = []
+    for use_prefetch in (False, True):
+        _, net = build(variant)
+        tr = DenseBoxTrainer(net.cuda(), B, lr=1e-7, dropout=False, use_cuda_graph=True)
+        losses = []
+        if use_prefetch:
+            tr.prefetch(batches[0][0], batches[0][1], rand_neg_idx=batches[0][2])
+        for i, (x, bbox, rand) in enumerate(batches):
+            loss = tr.step(x, bbox, rand_neg_idx=rand)
+            if use_prefetch and i + 1 < len(batches):
+                nx = batches[i + 1]
+                tr.prefetch(nx[0], nx[1], rand_neg_idx=nx[2])
+            losses.append(loss.item())
+        out.append(losses)
+    assert out[0] == out[1], out
