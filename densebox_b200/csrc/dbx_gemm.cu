@@ -484,6 +484,7 @@ int conv_fprop(const Act& x, const void* wk, int R, int S, int pad, const Act& o
 
   Tile t = choose_tile(out.W, out.H, out.N, false);
   int tma_epi = epi.out_fp32 ? 0 : 1;
+  const bool bf16_out = !epi.out_fp32;
   { const char* e = getenv("DBX_DIRECT_EPI"); if (e && e[0] == '1' && epi.aux_mode != 3) tma_epi = 0; }  // A/B switch
   // Column-box mode (see the kernel) for the 3x3 pad-1 layers on maps that 8 x 16 tiles cover without much waste.
   // Measured (tools/bench_colbox.py, B = 32, generic -> colbox + CTA pairs, TFLOP/s): conv2_1 dgrad 557 -> 1004,
@@ -492,11 +493,11 @@ int conv_fprop(const Act& x, const void* wk, int R, int S, int pad, const Act& o
   int colbox = 0;
   int colbox_max_n = 256;
   { const char* e = getenv("DBX_COLBOX_MAX_N"); if (e) colbox_max_n = atoi(e); }
-  if (R == 3 && S == 3 && pad == 1 && tma_epi && block_n <= colbox_max_n && block_n % 32 == 0 && epi.aux_mode != 3) {
+  if (R == 3 && S == 3 && pad == 1 && bf16_out && block_n <= colbox_max_n && block_n % 32 == 0 && epi.aux_mode != 3) {
     const double cover = (double)out.W * out.H / ((double)((out.W + 7) / 8 * 8) * ((out.H + 15) / 16 * 16));
     colbox = cover >= 0.87 ? 1 : 0;   // 60 x 60 and 30 x 30 maps: 0.879 (measured: still +30 % on conv3_1 dgrad)
   }
-  { const char* e = getenv("DBX_COLBOX_FPROP"); if (e && R == 3 && S == 3 && pad == 1 && tma_epi) colbox = atoi(e) != 0; }
+  { const char* e = getenv("DBX_COLBOX_FPROP"); if (e && R == 3 && S == 3 && pad == 1 && bf16_out) colbox = atoi(e) != 0; }
   if (colbox) {
     t.tw = 8; t.th = 16; t.tn = 1;
     t.tiles_w = (out.W + 7) / 8; t.tiles_h = (out.H + 15) / 16; t.tiles_n = out.N;
@@ -506,7 +507,7 @@ int conv_fprop(const Act& x, const void* wk, int R, int S, int pad, const Act& o
   // issue-bound and pairing changed nothing.  ConvEpilogue::force_cta2 = 0 or DBX_CTA2=0 switches it off.)
   int cta2_min_n = colbox ? 64 : 256;
   { const char* e = getenv("DBX_CTA2_MIN_N"); if (e) cta2_min_n = atoi(e); }
-  const bool cta2_ok = tma_epi && block_n >= cta2_min_n && block_n % 32 == 0 && t.count() >= 2 && num_sms() >= 2;
+  const bool cta2_ok = bf16_out && block_n >= cta2_min_n && block_n % 32 == 0 && t.count() >= 2 && num_sms() >= 2;
   int cta2 = (cta2_ok && epi.force_cta2 != 0) ? 1 : 0;
   { const char* e = getenv("DBX_CTA2"); if (e && cta2_ok) cta2 = e[0] == '1'; }  // A/B switch for measurements
   CUtensorMap tmA, tmB, tmO, tmX;
