@@ -479,8 +479,22 @@ int conv_fprop(const Act& x, const void* wk, int R, int S, int pad, const Act& o
       if (rc != DBX_ERR_ARG) return rc;
     }
   }
+  const bool auto_n = block_n <= 0;
   if (block_n <= 0) block_n = out.C >= 256 ? 256 : out.C;
   if (block_n % 16 || block_n > 256 || block_n < 16) return DBX_ERR_ARG;
+  if (auto_n && R == 3 && S == 3 && pad == 1 && out.C >= 256 && out.C % 128 == 0 && !epi.out_fp32) {
+    // Wave quantisation: a CTA pair takes whole (256-pixel x block_n) units.  On the 30 x 30 maps at B = 32 there are
+    // 256 such units of width 256 for 74 pairs = 3.46 waves, i.e. 4 unit times; 128-wide units give 6.92 -> 7 half
+    // unit times.  Measured (tools/bench_blockn.py): conv4_2 1 081 -> 1 475 TFLOP/s, conv4_1 956 -> 1 123; on the
+    // 60 x 60 maps (6.92 waves at 256) nothing changes.  128-wide units re-read the input boxes twice: +4 % cost.
+    const long m_pairs = ((long)((out.W + 7) / 8) * ((out.H + 15) / 16) * out.N + 1) / 2;
+    const long pairs = num_sms() / 2 > 0 ? num_sms() / 2 : 1;
+    const long u256 = m_pairs * ((out.C + 255) / 256), u128 = m_pairs * (out.C / 128);
+    const double c256 = (double)((u256 + pairs - 1) / pairs) * 256.0;
+    const double c128 = (double)((u128 + pairs - 1) / pairs) * 128.0 * 1.04;
+    const char* e = getenv("DBX_AUTO_BLOCK_N");
+    if (c128 < c256 && !(e && e[0] == '0')) block_n = 128;
+  }
 
   Tile t = choose_tile(out.W, out.H, out.N, false);
   int tma_epi = epi.out_fp32 ? 0 : 1;
