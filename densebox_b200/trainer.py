@@ -51,6 +51,11 @@ class DenseBoxTrainer:
         self._rng = self.eng.buffer("rng", torch.int64)
         drop_elems = self.eng.buffer("drop", torch.bfloat16).numel()
         self._rng_stride = (drop_elems + 127) // 128  # Philox calls consumed by one step
+        # {seed, offset}: the offset advances by one stride per step INSIDE the captured step (device side, no
+        # per-step host write); it starts one stride before 0 so that step n draws from offset n * stride
+        self._rng[0] = seed
+        self._rng[1] = -self._rng_stride
+        self._rng_off = self._rng[1:2]
         # prefetch(): host batch i+1 is copied on a side stream into staging buffers while step i computes
         self._pf = None            # {"x": ..., "bbox": ..., ...} staging tensors (lazily allocated)
         self._pf_key = None        # identity of the host tensors staged last
@@ -129,6 +134,8 @@ class DenseBoxTrainer:
 
     def _fwd_loss_bwd(self):
         e = self.eng
+        if self.dropout:
+            self._rng_off.add_(self._rng_stride)  # a fresh dropout mask per step (captured with the step)
         e.forward(self.x, dropout_mode=3 if self.dropout else 0)  # Philox in the epilogues, state in the rng region
         self._loss()
         e.backward()
@@ -146,6 +153,8 @@ class DenseBoxTrainer:
         e, dist = self.eng, torch.distributed
 
         def fwd():
+            if self.dropout:
+                self._rng_off.add_(self._rng_stride)
             e.forward(self.x, dropout_mode=3 if self.dropout else 0)
             e.join()
 
@@ -198,9 +207,6 @@ class DenseBoxTrainer:
                 self._stage(self.lm_rand, lm_rand_neg_idx)
         if staged:  # the staging buffers may be refilled once these device-to-device copies are done
             self._pf_free.record(torch.cuda.current_stream(self.device))
-        if self.dropout:  # a fresh mask per step: advance the Philox counter offset (device side, graph safe)
-            self._rng[0] = self.seed
-            self._rng[1] = self.step_no * self._rng_stride
         graph_ok = self.use_graph and self.step_no >= 1  # step 0 runs eagerly (one-time inits, SGD first-step flag)
         if self.world > 1:
             self._step_dp(graph_ok)
