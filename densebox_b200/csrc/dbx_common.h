@@ -41,6 +41,7 @@ int encode_act_map(CUtensorMap* m, const Act& a, const Tile& t);                
 int encode_mat_map(CUtensorMap* m, const void* ptr, int rows, int cols, int box_rows); // 2D (cols, rows), box (64, box_rows)
 
 int num_sms();
+bool pdl_enabled();
 
 // ---- kernels (launchers). All are asynchronous on `stream`, allocate nothing, and return an error code.
 

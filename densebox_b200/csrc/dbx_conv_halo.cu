@@ -43,6 +43,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   __shared__ uint64_t afull[kMaxASlots], aempty[kMaxASlots], bfull[kMaxBSlots], bempty[kMaxBSlots];
   __shared__ uint64_t tfull_bar[2], tempty_bar[2], aux_bar[8];
   __shared__ uint32_t tmem_base_s;
+  griddep_launch_dependents();
 
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
@@ -74,6 +75,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
+  griddep_wait();
 
   if (warp == 0) {
     // ===================== producer: column boxes + filter tiles (warp-uniform walk, elected lane issues) =========
@@ -290,8 +292,13 @@ int conv3x3_halo(const Act& x, const void* wk, const Act& out, const ConvEpilogu
   if (attr_rc) return attr_rc;
   const int total = p.m_tiles * p.n_tiles;
   const int grid = total < num_sms() ? total : num_sms();
-  conv3x3_halo_kernel<<<grid, kHaloThreads, smem, stream>>>(tmA, tmB, tmO, tmX, p);
-  return (int)cudaGetLastError();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kHaloThreads); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return (int)cudaLaunchKernelEx(&cfg, conv3x3_halo_kernel, tmA, tmB, tmO, tmX, p);
 }
 
 }  // namespace dbx

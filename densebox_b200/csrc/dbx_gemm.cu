@@ -27,6 +27,15 @@ static constexpr int kSmemBudget = 230400;      // usable dynamic smem (227 KB -
 static constexpr int kEpiBuf = 16384;           // one epilogue staging buffer: 128 rows x 64 bf16 channels
 
 // ------------------------------------------------------------------------------------------------ host helpers
+// Programmatic dependent launch of the tensor kernels: opt-in (DBX_PDL=1).  Measured +0.75 % on the sustained step
+// (the prologue of a persistent kernel overlaps the tail of the previous one); all parity tests pass with it, but
+// the gain does not justify making early-scheduled CTAs the default before it has soaked on multi-GPU runs.
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("DBX_PDL"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v == 1;
+}
+
 int num_sms() {
   static int n = 0;
   if (n == 0) {
@@ -150,6 +159,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t full_bar[kMaxStages], empty_bar[kMaxStages], tfull_bar[2], tempty_bar[2], aux_bar[8];
   __shared__ uint32_t tmem_base_s;
+  griddep_launch_dependents();  // persistent grid, fully resident: the next kernel may take the SMs we leave
 
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
@@ -201,6 +211,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if constexpr (cta2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
+  griddep_wait();  // everything above (barriers, TMEM, descriptors) overlapped the previous kernel's tail
 
   // Shared-window addresses are computed once: the hot loops below must stay a few dozen instructions per K block,
   // a single warp issues them back to back (round 1 profile: the old MMA loop spent ~650 cycles/K-block on address
@@ -617,7 +628,7 @@ int conv_fprop(const Act& x, const void* wk, int R, int S, int pad, const Act& o
   cfg.blockDim = dim3(kFpropThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   int grid;
   if (cta2) {
     const int units = ((p.m_tiles + 1) / 2) * p.n_tiles;
@@ -629,7 +640,9 @@ int conv_fprop(const Act& x, const void* wk, int R, int S, int pad, const Act& o
   }
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = cta2 ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr; cfg.numAttrs = 2;
   cfg.gridDim = dim3(grid);
   rc = (int)cudaLaunchKernelEx(&cfg, fn, tmA, tmB, tmO, tmX, p);
   if (rc == 0 && colsum_after) rc = colsum(out, epi.colsum, stream);
@@ -658,6 +671,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t full_bar[kMaxStages], empty_bar[kMaxStages], tfull_bar[2], tempty_bar[2];
   __shared__ uint32_t tmem_base_s;
+  griddep_launch_dependents();
 
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
@@ -691,6 +705,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
   if constexpr (cta2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
+  griddep_wait();
 
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
@@ -903,10 +918,12 @@ int conv_wgrad(const Act& x, const Act& dy, int R, int S, int pad, float* dw, in
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = cta2 ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr; cfg.numAttrs = 2;
   cfg.gridDim = dim3((cta2 ? 2 : 1) * (total < workers ? total : workers));
   if (cta2) return (int)cudaLaunchKernelEx(&cfg, conv_wgrad_kernel<true>, tmDy, tmX, p);
   return (int)cudaLaunchKernelEx(&cfg, conv_wgrad_kernel<false>, tmDy, tmX, p);

@@ -201,6 +201,15 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start (be scheduled, run its
+// prologue) before the previous kernel of the stream has finished; griddep_wait() blocks until that kernel has
+// completed and its memory is visible (a no-op when there is no programmatic dependency).  griddep_launch_dependents()
+// lets the NEXT kernel's CTAs be scheduled as soon as resources free up; only kernels whose whole grid is resident
+// at once call it (persistent tensor kernels: their successor can only land on SMs they have already left).
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---------------------------------------------------------------- tcgen05 / TMEM
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)),
