@@ -336,9 +336,11 @@ __global__ void __launch_bounds__(256) upsample_bwd_kernel(Act dout, Act y, int 
   __shared__ float xwt[kUpMaxW][kUpMaxTaps];
   const int cc = din.C / 8;
   const int iy = (int)(blockIdx.x % din.H), n = (int)(blockIdx.x / din.H);
+  // candidates: outputs whose source coordinate lies within (i - 1, i + 1), +-1 for rounding
   if (threadIdx.x == 0) {
-    int k = 0;
-    for (int oy = 0; oy < dout.H; ++oy) {
+    int k = 0, lo = 0, hi = dout.H - 1;
+    if (sh > 0.f) { lo = max(0, (int)floorf((iy - 1) / sh) - 1); hi = min(dout.H - 1, (int)ceilf((iy + 1) / sh) + 1); }
+    for (int oy = lo; oy <= hi; ++oy) {
       const Lin l = lin_coord(oy, sh, din.H);
       const float w = (l.i0 == iy ? l.l0 : 0.f) + (l.i1 == iy ? l.l1 : 0.f);
       if (w != 0.f && k < kUpMaxTaps) { yidx[k] = oy; ywt[k] = w; ++k; }
@@ -346,8 +348,9 @@ __global__ void __launch_bounds__(256) upsample_bwd_kernel(Act dout, Act y, int 
     ycnt = k;
   }
   for (int ix = threadIdx.x; ix < din.W; ix += 256) {
-    int k = 0;
-    for (int ox = 0; ox < dout.W; ++ox) {
+    int k = 0, lo = 0, hi = dout.W - 1;
+    if (sw > 0.f) { lo = max(0, (int)floorf((ix - 1) / sw) - 1); hi = min(dout.W - 1, (int)ceilf((ix + 1) / sw) + 1); }
+    for (int ox = lo; ox <= hi; ++ox) {
       const Lin l = lin_coord(ox, sw, din.W);
       const float w = (l.i0 == ix ? l.l0 : 0.f) + (l.i1 == ix ? l.l1 : 0.f);
       if (w != 0.f && k < kUpMaxTaps) { xidx[ix][k] = ox; xwt[ix][k] = w; ++k; }
