@@ -133,6 +133,38 @@ __device__ void topk_mark(const uint32_t* keys, int k, unsigned char* sel, uint3
   __syncthreads();
 }
 
+// k = 1: the largest key, lowest index among equals (what topk_mark(keys, 1, ...) marks) — one arg-max reduction
+// instead of a 4-pass radix select.  `ws` = 2 * LT/32 words of shared memory.  All LT threads call this.
+__device__ void top1_mark(const uint32_t* keys, unsigned char* sel, uint32_t* ws) {
+  uint32_t bk = 0u; int bi = MAPN;  // (key, index): larger key wins, then smaller index
+  for (int i = threadIdx.x; i < MAPN; i += LT) {
+    const uint32_t key = keys[i];
+    if (key > bk || (key == bk && i < bi)) { bk = key; bi = i; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const uint32_t ok = __shfl_xor_sync(0xffffffffu, bk, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ok > bk || (ok == bk && oi < bi)) { bk = ok; bi = oi; }
+  }
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) { ws[2 * w] = bk; ws[2 * w + 1] = (uint32_t)bi; }
+  __syncthreads();
+  if (w == 0) {
+    bk = lane < LT / 32 ? ws[2 * lane] : 0u;
+    bi = lane < LT / 32 ? (int)ws[2 * lane + 1] : MAPN;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const uint32_t ok = __shfl_xor_sync(0xffffffffu, bk, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ok > bk || (ok == bk && oi < bi)) { bk = ok; bi = oi; }
+    }
+    if (lane == 0 && bi < MAPN) sel[bi] = 1;
+  }
+  __syncthreads();
+}
+
 __global__ void __launch_bounds__(LT) loss_kernel(const LossParams p) {
   __shared__ uint32_t keys[MAPN];
   __shared__ unsigned char mask[MAPN];
@@ -222,7 +254,7 @@ __global__ void __launch_bounds__(LT) loss_kernel(const LossParams p) {
         lmm[k][i] = g ? 1 : 0;
       }
       __syncthreads();
-      topk_mark(keys, 1, lmm[k], hist, sc);
+      top1_mark(keys, lmm[k], hist);  // torch.topk(k=1) (:2672): an arg-max
       if (tid == 0 && p.lm_rand_idx) {
         const long long idx = p.lm_rand_idx[(size_t)b * 4 + k];
         if (idx >= 0 && idx < MAPN) lmm[k][idx] = 1;
