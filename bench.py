@@ -44,7 +44,7 @@ def traffic_from_profile(variant, B):
     if variant != "densebox" or B != 32 or not os.path.exists(p):
         return None
     d = json.load(open(p))
-    return {"value": d["dram_mb_per_launch"], "unit": "MB per launch", "launches": d["launches"], "source": d["source"]}
+    return {"bytes": int(d["dram_mb_per_launch"] * 1e6), "launches": d["launches"], "source": d["source"]}
 
 
 class ClockSampler:
@@ -304,11 +304,13 @@ def main():
         conv = [fam.get("fprop", [0, 0, 0]), fam.get("dgrad", [0, 0, 0])]
         fl = conv[0][0] + conv[1][0]; tm = conv[0][1] + conv[1][1]
         ach = fl / tm * 1e-9
+        tp = traffic_from_profile(variant, B)
         roof = {"kernel": "conv_fprop_kernel + conv3x3_halo_kernel (tcgen05 implicit GEMM: %d fprop + %d dgrad launches per step)"
                           % (conv[0][2], conv[1][2]),
                 "bound": "tensor", "achieved": round(ach, 1), "peak": pk["tf_sustained"], "unit": "TFLOP/s",
-                "frac": round(ach / pk["tf_sustained"], 4), "traffic": traffic_from_profile(variant, B),
-                "peak_source": pk["source"],
+                "frac": round(ach / pk["tf_sustained"], 4), "traffic": (tp or {}).get("bytes"),
+                "traffic_unit": "DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full)",
+                "traffic_source": (tp or {}).get("source"), "peak_source": pk["source"],
                 "algorithmic_gflop_per_launch_avg": round(fl / max(conv[0][2] + conv[1][2], 1) * 1e-9, 2),
                 "avg_launch_ms": round(tm / max(conv[0][2] + conv[1][2], 1), 4),
                 "step_tflops": round(GFLOP_TRAIN[variant] * B / ms, 1),
