@@ -267,3 +267,24 @@ def test_trainer_prefetch_matches_direct_step():
             losses.append(loss.item())
         out.append(losses)
     assert out[0] == out[1], out
+
+
+@pytest.mark.parametrize("variant,H,W", [("densebox", 264, 328), ("lmloc", 136, 200)])
+def test_inference_forward_other_sizes(variant, H, W):
+    """Inference forward (eval, no grad) on non-square inputs whose maps are NOT multiples of the 8 x 16 column-box
+    tiles (33 x 41 at conv4 for 264 x 328): ragged tiles, the pairs layout of conv1_1, CTA pairs with an odd tile
+    count.  Head maps within 3e-2 of the oracle's largest entry (bf16 storage, same bound as the 240 x 240 test)."""
+    _, net = build(variant)
+    net = net.cuda().eval()
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(2, 3, H, W, generator=g).bfloat16().float()
+    with torch.no_grad():
+        outs = net(x.cuda())
+    P = oracle_params(net, variant)
+    with torch.no_grad():
+        ref = O.forward(P, x, variant)
+    assert len(outs) == len(ref)
+    for o, r in zip(outs, ref):
+        assert tuple(o.shape) == tuple(r.shape)
+        err = (o.float().cpu() - r).abs().max().item()
+        assert err <= 3e-2 * r.abs().max().item(), (variant, tuple(o.shape), err, r.abs().max().item())
