@@ -94,7 +94,9 @@ class DenseBoxTrainer:
     def prefetch(self, x, bbox, vertices=None, labels=None, rand_neg_idx=None, lm_rand_neg_idx=None):
         """Start the host->device copy of the NEXT batch (pinned host tensors) on a side stream; a following
         `step()` called with the same tensors finds them in device staging buffers and only pays a device-to-device
-        copy.  The usual prefetching-loader pattern: `step(batch_i)`, `prefetch(batch_i+1)`, then read the loss."""
+        copy.  The usual prefetching-loader pattern: `step(batch_i)`, `prefetch(batch_i+1)`, then read the loss.
+        The staged copy is matched by tensor identity (data pointer + shape): do not modify the host tensors between
+        `prefetch()` and the `step()` that consumes them."""
         args = {"x": x, "bbox": bbox, "vertices": vertices, "labels": labels, "rand": rand_neg_idx,
                 "lm_rand": lm_rand_neg_idx}
         if not all(v is None or (torch.is_tensor(v) and not v.is_cuda) for v in args.values()):
