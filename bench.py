@@ -1,14 +1,23 @@
 #!/usr/bin/env python
 """bench.py — training patches/s of the DenseBox hot path at 240x240 (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--variant densebox|lm|lmloc]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--records all|main]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
 
-Workload (N=1): BASELINE.json configs[1] — batch 32 x 240x240, DenseBox (score + bbox heads), bf16 tensor-core math,
-fp32 accumulation/master weights, synthetic data, seeded random-init weights.  Weak scaling: 32 patches per GPU.
-A step = H2D-free forward + fused loss + backward + (N>1: gradient SUM all-reduce) + SGD on device-resident inputs
-(`value`), and the same through the public API with HOST pinned inputs and a D2H read of the loss (`e2e`).
+Headline workload (every N): BASELINE.json configs[1] — 32 patches of 240x240 per GPU, DenseBox (score + bbox heads),
+bf16 tensor-core math, fp32 accumulation / master weights, synthetic data, seeded random-init weights; weak scaling.
+A step = forward + fused loss + backward + (N>1: gradient SUM all-reduce) + SGD.
+  value : device-resident inputs (the batch is copied device-to-device into the trainer's input slot each step)
+  e2e   : the same through the public API with HOST pinned inputs — every step copies its batch host -> device
+          (prefetched on a side stream) and reads its loss back (asynchronously, consumed one step later)
+Further records on the same JSON line (driver-run evidence for the other BASELINE configs):
+  N = 1 : parity (loss of the first bench batch vs the CPU oracle fed the same Philox dropout mask), config3 (B=64
+          DenseBoxLM), config5 (1024x1024 B=16 DenseBoxLMLOC inference + top-10 decode + NMS, images/s), sustained
+          (>= 300 steps of the headline workload with its own clock record), dropin (the nn.Module path: net(x) ->
+          densebox_loss -> backward -> torch.optim.SGD.step)
+  N > 1 : config4 (DenseBoxLM, 32 per GPU, data parallel: value, the same variant on one GPU of this box, exposed
+          communication per step = step time with minus without the all-reduces)
 `--impl reference` times the reference's CPU implementation of the same step (the oracle port — the reference is
 pure Python/torch and cannot travel to the GPU box) on the host cores.
 """
@@ -24,7 +33,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 GFLOP_TRAIN = {"densebox": 125.732, "lm": 134.639, "lmloc": 143.221}  # SURVEY.md §8(d), fwd+dgrad+wgrad per patch
-PER_GPU_BATCH = {"densebox": 32, "lm": 32, "lmloc": 32}
+GFLOP_INFER_1024 = {"lmloc": 871.2}                                     # BASELINE.md §2, forward per 1024x1024 image
+CLS = {"densebox": "DenseBox", "lm": "DenseBoxLM", "lmloc": "DenseBoxLMLOC"}
+METRIC = "training patches/sec at 240x240"
 
 
 def peaks():
@@ -36,15 +47,25 @@ def peaks():
     return {"hbm_gbs": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
 
 
+def headline_config(world, graph=True):
+    """The `config` object of the headline line; identical in both arms (the reference arm samples it)."""
+    return {"workload": "configs[1]: batch=32 240x240 bf16 training step, score+bbox heads (DenseBox)",
+            "variant": "densebox", "per_gpu_batch": 32, "global_batch": 32 * world, "parallelism": "dp%d" % world,
+            "step": "fwd + fused loss + bwd + grad allreduce(sum) + SGD",
+            "cache": "inputs larger than L2: one step streams ~3.6 GB of activations per GPU >> 126 MB L2 (no flush needed)",
+            "cuda_graph": graph, "weights": "seeded vgg19(weights=None) + xavier heads",
+            "optimizer": "SGD lr=1e-9 m=0.9 wd=5e-8 (DenseBox.py:2821-2824)"}
+
+
 def traffic_from_profile(variant, B):
-    """DRAM bytes per launch of the dominant kernel family from the committed `ncu --set full` capture
-    (profiles/ncu_traffic_r1.json: dram__bytes_read.sum + dram__bytes_write.sum averaged over the 25 fprop/dgrad
-    launches of one B=32 DenseBox step); null for any other workload."""
-    p = os.path.join(ROOT, "profiles", "ncu_traffic_r1.json")
-    if variant != "densebox" or B != 32 or not os.path.exists(p):
-        return None
-    d = json.load(open(p))
-    return {"bytes": int(d["dram_mb_per_launch"] * 1e6), "launches": d["launches"], "source": d["source"]}
+    """DRAM bytes per launch of the dominant kernel family from the committed `ncu --set full` capture: null for any
+    workload other than the one profiled."""
+    for name in ("ncu_traffic_r2.json", "ncu_traffic_r1.json"):
+        p = os.path.join(ROOT, "profiles", name)
+        if variant == "densebox" and B == 32 and os.path.exists(p):
+            d = json.load(open(p))
+            return {"bytes": int(d["dram_mb_per_launch"] * 1e6), "launches": d["launches"], "source": d["source"]}
+    return None
 
 
 class ClockSampler:
@@ -76,13 +97,18 @@ class ClockSampler:
 
     def __exit__(self, *a):
         self.t1 = time.time()
+
+    def stop(self):
         if self.proc:
             time.sleep(0.12)
             self.proc.terminate()
             self.t.join(timeout=2)
+            self.proc = None
 
-    def summary(self):
-        inside = [r for t, r in self.rows if self.t0 is not None and self.t0 <= t <= self.t1 + 0.06]
+    def summary(self, t0=None, t1=None):
+        t0 = self.t0 if t0 is None else t0
+        t1 = self.t1 if t1 is None else t1
+        inside = [r for t, r in self.rows if t0 is not None and t0 <= t <= t1 + 0.06]
         sm, mx, pw, reasons = [], 0, [], set()
         for r in inside:
             try:
@@ -154,27 +180,302 @@ def cpu_step_time(variant, B, steps, warmup, threads):
 def run_reference(args, rank):
     if rank != 0:
         return
-    variant = args.variant
+    variant = "densebox"
     threads = os.cpu_count() or 1
     B = 4
     times, loss = cpu_step_time(variant, B, args.steps, args.warmup, threads)
     total = sum(times)
     v = B * len(times) / total
     line = {
-        "metric": "training patches/sec at 240x240", "value": v, "unit": "patches/s", "n_gpus": args.gpus,
+        "metric": METRIC, "value": v, "unit": "patches/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-        "impl": "reference",
-        "config": {"workload": "configs[1]: DenseBox (score+bbox) 240x240 training step, fwd+loss+bwd+SGD",
-                   "variant": variant, "sample": "batch %d per step on the host CPU" % B},
+        "impl": "reference", "config": headline_config(args.gpus),
         "cpu_baseline": {"value": v, "unit": "patches/s", "cores": threads, "kind": "port",
-                         "sample": "%d steps of batch %d (oracle port of the reference loop body; the reference is "
-                                   "Python/torch and does not travel to the GPU box; label generation vectorised)"
-                                   % (len(times), B)},
+                         "sample": "%d steps, each a 4-patch sample of the 32-patch batch (fp32, all host threads; oracle "
+                                   "PORT of the reference loop body DenseBox.py:2843-2926 + torch.optim.SGD — the "
+                                   "reference is Python/torch and does not travel to the GPU box; its label generation "
+                                   "is vectorised here, so this is faster than the reference itself)" % len(times)},
         "e2e": {"value": v, "unit": "patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "loss": loss,
     }
     print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+class Ctx:
+    pass
+
+
+def make_net(variant, dev):
+    import torch
+    import densebox_b200
+    from oracle import densebox_oracle as O  # seeded weights recipe (shared with the CPU arm), outside any timed region
+    vgg = O.seeded_vgg19(0)
+    torch.manual_seed(1)
+    return getattr(densebox_b200, CLS[variant])(vgg).to(dev)
+
+
+def timed_steps(c, tr, batches, steps, host, sampler=None):
+    """`steps` training steps, CUDA events on the launching stream between two barriers; returns ms per step (this
+    rank) and the last loss.  host=True: pinned host batches through prefetch() + asynchronous loss read-back."""
+    import torch
+    nb = len(batches)
+
+    def kw(b):
+        return dict(vertices=b.get("vertices"), rand_neg_idx=b["rand"], lm_rand_neg_idx=b.get("lm_rand"))
+
+    c.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.time()
+    e0.record()
+    last = None
+    if host:
+        tr.prefetch(batches[0]["x"], batches[0]["bbox"], **kw(batches[0]))
+        prev = None
+        for i in range(steps):
+            b, nxt = batches[i % nb], batches[(i + 1) % nb]
+            h = tr.step(b["x"], b["bbox"], async_loss=True, **kw(b))   # consumes the staged copy of this batch
+            tr.prefetch(nxt["x"], nxt["bbox"], **kw(nxt))               # H2D of the next batch, concurrent with this step
+            if prev is not None:
+                last = prev.item()                                      # D2H read of the previous step's loss
+            prev = h
+        last = prev.item()
+    else:
+        for i in range(steps):
+            b = batches[i % nb]
+            t = tr.step(b["x"], b["bbox"], **kw(b))
+        last = t
+    e1.record()
+    c.barrier()
+    t1 = time.time()
+    ms = e0.elapsed_time(e1) / steps
+    if not host:
+        last = float(last.item())
+    clocks = sampler.summary(t0, t1) if sampler is not None else None
+    return ms, last, clocks
+
+
+def max_over_ranks(c, vals):
+    import torch
+    t = torch.tensor(vals, device=c.dev, dtype=torch.float64)
+    if c.world > 1:
+        c.dist.all_reduce(t, op=c.dist.ReduceOp.MAX)
+    return [float(v) for v in t]
+
+
+def loss_parity(c, tr, net_params, variant, batch):
+    """The loss of the trainer's FIRST step (eager, Philox dropout from (seed, offset 0)) against the CPU oracle fed the
+    same bf16-rounded weights and the same dropout mask (materialised with dbx_dropout_mask).  Returns the record;
+    the step counts as the first warm-up step."""
+    import ctypes
+    import numpy as np
+    import torch
+    from densebox_b200._lib import check, lib, ptr, stream_ptr
+    from oracle import densebox_oracle as O
+    B = tr.B
+    loss0 = float(tr.step(batch["x"], batch["bbox"], vertices=batch.get("vertices"), rand_neg_idx=batch["rand"],
+                          lm_rand_neg_idx=batch.get("lm_rand")).item())
+    half, pos = tr.eng.loss_info()
+    heads = {"densebox": ["det", "loc"], "lm": ["det", "loc", "landmark"], "lmloc": ["det", "loc", "landmark", "lmloc"]}[variant]
+    nh = len(heads)
+    mask = torch.empty(B, 60, 60, 512 * nh, dtype=torch.bfloat16, device=c.dev)
+    check(lib().dbx_dropout_mask(ptr(mask), ctypes.c_ulonglong(mask.numel()), ctypes.c_ulonglong(tr.seed),
+                                 ctypes.c_ulonglong(0), stream_ptr()), "dropout_mask")
+    drop = {h: mask[..., 512 * i:512 * (i + 1)].permute(0, 3, 1, 2).float().cpu() for i, h in enumerate(heads)}
+    del mask
+    P = {k: (v.bfloat16().float() if k.endswith(".weight") else v) for k, v in net_params.items()}
+    t0 = time.time()
+    with torch.no_grad():
+        outs = O.forward(P, batch["x"].bfloat16().float(), variant, dropout=drop)
+        L_ref, info = O.loss(outs, variant, batch["bbox"].numpy(), batch["rand"].numpy(),
+                             vertices=batch["vertices"].numpy() if "vertices" in batch else None,
+                             lm_rand_idx=batch["lm_rand"].numpy() if "lm_rand" in batch else None)
+    L_ref = float(L_ref)
+    return {"loss": loss0, "oracle_loss": L_ref, "loss_rel_err": abs(loss0 - L_ref) / abs(L_ref), "tolerance": 1e-3,
+            "half": half, "oracle_half": info["half"], "pos": pos, "oracle_pos": info["pos"],
+            "batch": B, "variant": variant, "dropout": "Philox mask of the step, materialised and fed to the oracle",
+            "oracle_seconds": round(time.time() - t0, 1),
+            "what": "first step of the bench (train mode) vs oracle.forward+loss on the same bf16-rounded weights/inputs"}
+
+
+def kernel_profile(tr, variant, B, ms_step, pk):
+    """Per-kernel accounting of one eager step (CUDA events around every launch of the engine)."""
+    tr.eng.profile(True)
+    tr._fwd_loss_bwd()
+    tr.eng.sgd_step(tr.lr, tr.momentum, tr.weight_decay)
+    recs = tr.eng.profile_records()
+    tr.eng.profile(False)
+    fam = {}
+    for tag, fl, t_ms in recs:
+        k = tag.split(":")[0]
+        f = fam.setdefault(k, [0.0, 0.0, 0])
+        f[0] += fl; f[1] += t_ms; f[2] += 1
+    tot_ms = sum(f[1] for f in fam.values())
+    kern = {k: {"ms": round(f[1], 4), "share": round(f[1] / tot_ms, 4), "launches": f[2],
+                "tflops": round(f[0] / f[1] * 1e-9, 1) if f[0] > 0 and f[1] > 0 else None}
+            for k, f in sorted(fam.items(), key=lambda kv: -kv[1][1])}
+    conv = [fam.get("fprop", [0, 0, 0]), fam.get("dgrad", [0, 0, 0])]
+    fl = conv[0][0] + conv[1][0]; tm = conv[0][1] + conv[1][1]
+    ach = fl / tm * 1e-9
+    tp = traffic_from_profile(variant, B)
+    nl = max(conv[0][2] + conv[1][2], 1)
+    roof = {"kernel": "conv_fprop_kernel + conv3x3_halo_kernel (tcgen05 implicit GEMM: %d fprop + %d dgrad launches per step)"
+                      % (conv[0][2], conv[1][2]),
+            "bound": "tensor", "achieved": round(ach, 1), "peak": pk["tf_burst"], "unit": "TFLOP/s",
+            "frac": round(ach / pk["tf_burst"], 4),
+            "peak_kind": "burst cuBLAS bf16 (launches timed one by one with CUDA events in a sub-second region)",
+            "traffic": (tp or {}).get("bytes"),
+            "traffic_unit": "DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full)",
+            "traffic_source": (tp or {}).get("source"), "peak_source": pk["source"],
+            "algorithmic_gflop_per_launch_avg": round(fl / nl * 1e-9, 2), "avg_launch_ms": round(tm / nl, 4),
+            "step_tflops": round(GFLOP_TRAIN[variant] * B / ms_step, 1),
+            "step_frac": round(GFLOP_TRAIN[variant] * B / ms_step / pk["tf_burst"], 4)}
+    return roof, kern
+
+
+def run_training(c, variant, B, steps, warmup, pg, graph=True, parity=False, profile=False, e2e=True, exposed=False):
+    """One trainer, one workload: returns the record (rank 0 fills everything, other ranks a subset)."""
+    import torch
+    import densebox_b200
+    from oracle import densebox_oracle as O
+    world = c.world if pg is not None else 1
+    net = make_net(variant, c.dev)
+    net_params = O.params_from_state_dict(net.state_dict(), variant) if parity else None
+    tr = densebox_b200.DenseBoxTrainer(net, B, lr=1e-9, momentum=0.9, weight_decay=5e-8, process_group=pg,
+                                       use_cuda_graph=graph, dropout=True, device=c.dev)
+    nb = 4
+    batches = synth(variant, B, c.rank, nb)
+    dev_batches = [{k: v.to(c.dev) for k, v in b.items()} for b in batches]
+    rec = {"variant": variant, "per_gpu_batch": B, "n_gpus": world, "steps": steps, "warmup": warmup}
+    l0 = tr.eng.launch_count()
+    if parity and c.rank == 0:
+        rec["parity"] = loss_parity(c, tr, net_params, variant, batches[0])
+    else:
+        b = dev_batches[0]
+        tr.step(b["x"], b["bbox"], vertices=b.get("vertices"), rand_neg_idx=b["rand"], lm_rand_neg_idx=b.get("lm_rand"))
+    # launches of one step: the engine's own count + the dropout counter update + the loss-ring copy (+ count kernel)
+    rec["gpu_launches_per_step"] = int(tr.eng.launch_count() - l0 + (1 if tr.dropout else 0) + 1 + (1 if world > 1 else 0))
+    for i in range(max(warmup, 3)):
+        b = dev_batches[i % nb]
+        tr.step(b["x"], b["bbox"], vertices=b.get("vertices"), rand_neg_idx=b["rand"], lm_rand_neg_idx=b.get("lm_rand"))
+    ms, loss, clocks = timed_steps(c, tr, dev_batches, steps, host=False, sampler=c.sampler)
+    vals = [ms]
+    if e2e:
+        for i in range(3):  # warm the host path: staging copies, the graphs of both slots, pinned loss ring
+            b = batches[i % nb]
+            tr.step(b["x"], b["bbox"], vertices=b.get("vertices"), rand_neg_idx=b["rand"], lm_rand_neg_idx=b.get("lm_rand"))
+        ms_e2e, _, _ = timed_steps(c, tr, batches, steps, host=True)
+        vals.append(ms_e2e)
+    if exposed and world > 1:
+        tr._skip_allreduce = True   # measurement only: the same step without its two exchanges
+        for i in range(2):
+            b = dev_batches[i % nb]
+            tr.step(b["x"], b["bbox"], vertices=b.get("vertices"), rand_neg_idx=b["rand"], lm_rand_neg_idx=b.get("lm_rand"))
+        ms_nc, _, _ = timed_steps(c, tr, dev_batches, steps, host=False)
+        tr._skip_allreduce = False
+        vals.append(ms_nc)
+    vals = max_over_ranks(c, vals)
+    ms = vals[0]
+    rec.update({"value": round(world * B / (ms * 1e-3), 1), "unit": "patches/s", "ms_per_step": round(ms, 4),
+                "loss": loss, "clocks": clocks, "workspace_gb": round(tr.eng.workspace_bytes / 1e9, 2),
+                "step_tflops_per_gpu": round(GFLOP_TRAIN[variant] * B / ms, 1)})
+    if e2e:
+        h2d = sum(v.numel() * v.element_size() for v in batches[0].values())
+        rec["e2e"] = {"value": round(world * B / (vals[1] * 1e-3), 1), "unit": "patches/s", "h2d_bytes_per_step": h2d,
+                      "d2h_bytes_per_step": 4, "ms_per_step": round(vals[1], 4),
+                      "how": "DenseBoxTrainer.prefetch/step on pinned host tensors; loss read back asynchronously one step later"}
+    if exposed and world > 1:
+        rec["exposed_comm_us_per_step"] = round((ms - vals[-1]) * 1e3, 1)
+        rec["ms_per_step_without_allreduce"] = round(vals[-1], 4)
+    if profile and c.rank == 0:
+        rec["roofline"], rec["kernels"] = kernel_profile(tr, variant, B, ms, c.pk)
+    c.keep = (tr, net, batches, dev_batches)
+    return rec
+
+
+def run_sustained(c, steps):
+    """>= 300 steps of the headline workload on the trainer of the main run: the power-capped steady state."""
+    tr, net, batches, dev_batches = c.keep
+    ms, loss, clocks = timed_steps(c, tr, dev_batches, steps, host=False, sampler=c.sampler)
+    B = tr.B
+    tf = GFLOP_TRAIN["densebox"] * B / ms
+    return {"steps": steps, "value": round(B / (ms * 1e-3), 1), "unit": "patches/s", "ms_per_step": round(ms, 4),
+            "clocks": clocks, "step_tflops": round(tf, 1), "peak": c.pk["tf_sustained"],
+            "peak_kind": "sustained cuBLAS bf16 (seconds-long loop under the power cap)",
+            "step_frac": round(tf / c.pk["tf_sustained"], 4), "loss": loss}
+
+
+def run_inference(c, variant="lmloc", N=16, HW=1024, steps=5, warmup=2):
+    """configs[4]: forward of a 1024x1024 batch + per-image top-10 decode + NMS 0.4 (test_lmloc DenseBox.py:3565-3647)."""
+    import torch
+    from densebox_b200 import decode_nms
+    net = make_net(variant, c.dev).eval()
+    x_host = torch.randn(N, 3, HW, HW, generator=torch.Generator().manual_seed(7)).pin_memory()
+    x_dev = x_host.to(c.dev)
+
+    def once(x):
+        with torch.no_grad():
+            score, rf, loc, lm, lmloc = net(x)
+        return decode_nms(rf, loc, lmloc, K=10, nms_thresh=0.4)  # returns host arrays: the detections leave the GPU
+
+    for _ in range(warmup):
+        dets = once(x_dev)
+    out = {}
+    for name, src in (("value", x_dev), ("e2e", x_host)):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            dets = once(src.to(c.dev, non_blocking=True) if src is x_host else src)
+        e1.record()
+        torch.cuda.synchronize()
+        out[name] = e0.elapsed_time(e1) / steps
+    eng = next(iter(net._engines.values()))
+    tf = GFLOP_INFER_1024[variant] * N / out["value"]
+    rec = {"workload": "configs[4]: inference forward 1024x1024, batch 16, heads + top-10 decode + NMS 0.4", "variant": variant,
+           "batch": N, "value": round(N / (out["value"] * 1e-3), 1), "unit": "images/s", "ms_per_batch": round(out["value"], 3),
+           "e2e": {"value": round(N / (out["e2e"] * 1e-3), 1), "unit": "images/s",
+                   "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": N * 10 * 14 * 4,
+                   "how": "pinned host batch copied in the timed loop (not overlapped), detections copied back"},
+           "gflop_per_image": GFLOP_INFER_1024[variant], "tflops": round(tf, 1), "peak": c.pk["tf_burst"],
+           "frac": round(tf / c.pk["tf_burst"], 4), "kept_per_image": [int(len(d)) for d in dets][:4],
+           "workspace_gb": round(eng.workspace_bytes / 1e9, 2), "steps": steps, "warmup": warmup}
+    net._engines.clear()
+    return rec
+
+
+def run_dropin(c, B=32, steps=10, warmup=3):
+    """The nn.Module path north_star names: net(x) -> densebox_loss -> .backward() -> torch.optim.SGD.step()."""
+    import torch
+    from densebox_b200 import densebox_loss
+    net = make_net("densebox", c.dev).train()
+    opt = torch.optim.SGD(net.parameters(), lr=1e-9, momentum=0.9, weight_decay=5e-8)
+    batches = [{k: v.to(c.dev) for k, v in b.items()} for b in synth("densebox", B, 0, 2)]
+
+    def step(b):
+        opt.zero_grad()
+        score, loc = net(b["x"])
+        L = densebox_loss(score, loc, b["bbox"], rand_neg_idx=b["rand"])
+        L.backward()
+        opt.step()
+        return L
+
+    for i in range(warmup):
+        step(batches[i % 2])
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        L = step(batches[i % 2])
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    rec = {"api": "DenseBox(vgg19)(x) -> densebox_loss(...) -> loss.backward() -> torch.optim.SGD.step() (eager, no CUDA graph)",
+           "batch": B, "value": round(B / (ms * 1e-3), 1), "unit": "patches/s", "ms_per_step": round(ms, 4),
+           "loss": float(L.item()), "steps": steps, "warmup": warmup}
+    net._engines.clear()
+    return rec
 
 
 def main():
@@ -183,8 +484,12 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--variant", default="densebox", choices=["densebox", "lm", "lmloc"])
-    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default 32)")
+    ap.add_argument("--variant", default="densebox", choices=["densebox", "lm", "lmloc"],
+                    help="headline variant (default: configs[1] DenseBox; other values are for ad-hoc measurements)")
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch of the headline run (default 32)")
+    ap.add_argument("--records", default="all", choices=["all", "main"],
+                    help="main: only the headline measurement (profiling runs)")
+    ap.add_argument("--sustained-steps", type=int, default=300)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
     args = ap.parse_args()
@@ -198,17 +503,24 @@ def main():
 
     import torch
     import torch.distributed as dist
-    import densebox_b200
-    from oracle import densebox_oracle as O  # cpu_baseline leg + seeded weights recipe only
 
     torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
+    c = Ctx()
+    c.dev = torch.device("cuda", local_rank)
+    c.rank, c.world, c.dist, c.pk = rank, world, dist, peaks()
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        dist.init_process_group("nccl", device_id=c.dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    c.barrier = barrier
     variant = args.variant
-    B = args.batch or PER_GPU_BATCH[variant]
-    pk = peaks()
+    B = args.batch or 32
+    full = args.records == "all"
 
     # ---- CPU baseline first (rank 0, N=1 only), before the GPU is busy
     cpu_base = None
@@ -217,129 +529,79 @@ def main():
         cb = 4
         times, _ = cpu_step_time(variant, cb, 3, 1, threads)
         cpu_base = {"value": cb / min(times), "unit": "patches/s", "cores": threads, "kind": "port",
-                    "sample": "best of 3 steps of batch %d (fwd+loss+bwd+SGD, fp32, oracle port of DenseBox.py "
-                              ":2843-2926; vectorised label generation)" % cb}
+                    "sample": "best of 3 steps of batch 4 (fwd+loss+bwd+SGD, fp32, oracle PORT of DenseBox.py "
+                              ":2843-2926 with vectorised label generation — faster than the reference itself)"}
 
-    vgg = O.seeded_vgg19(0)
-    torch.manual_seed(1)
-    net = getattr(densebox_b200, {"densebox": "DenseBox", "lm": "DenseBoxLM", "lmloc": "DenseBoxLMLOC"}[variant])(vgg)
-    net = net.to(dev)
+    c.sampler = ClockSampler(local_rank) if rank == 0 else None  # started now: its first rows arrive during the warm-up
     pg = dist.group.WORLD if world > 1 else None
-    tr = densebox_b200.DenseBoxTrainer(net, B, lr=1e-9, momentum=0.9, weight_decay=5e-8, process_group=pg,
-                                       use_cuda_graph=not args.no_graph, dropout=True, device=dev)
-    nb = 4
-    batches = synth(variant, B, rank, nb)
-    dev_batches = [{k: v.to(dev) for k, v in b.items()} for b in batches]
-
-    def step(b):
-        return tr.step(b["x"], b["bbox"], vertices=b.get("vertices"), rand_neg_idx=b["rand"],
-                       lm_rand_neg_idx=b.get("lm_rand"))
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    clk = ClockSampler(local_rank)  # started now: its first rows arrive during the warm-up
-    # ---- kernel launches per step (eager step 0 also does the one-time initialisation)
-    l0 = tr.eng.launch_count()
-    step(dev_batches[0])
-    launches_per_step = tr.eng.launch_count() - l0 + (1 if tr.dropout else 0) + (1 if world > 1 else 0)
-    for i in range(args.warmup):
-        step(dev_batches[i % nb])
-    # ---- timed: device-resident inputs
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with clk:
-        e0.record()
-        for i in range(args.steps):
-            loss_t = step(dev_batches[i % nb])
-        e1.record()
+    main_rec = run_training(c, variant, B, args.steps, args.warmup, pg, graph=not args.no_graph,
+                            parity=full and world == 1, profile=True, e2e=True, exposed=world > 1)
+    records = {}
+    if full and world == 1:
+        records["sustained"] = run_sustained(c, args.sustained_steps)
+    c.keep = None
+    torch.cuda.empty_cache()
+    if full and world == 1:
+        records["config3"] = run_training(c, "lm", 64, 10, 3, None, graph=not args.no_graph, parity=True, profile=False)
+        records["config3"]["workload"] = "configs[2]: batch=64 multi-task (score+bbox+4-landmark+refine, DenseBoxLM) bf16 training on 1xB200"
+        c.keep = None
+        torch.cuda.empty_cache()
+        records["config5"] = run_inference(c)
+        torch.cuda.empty_cache()
+        records["dropin"] = run_dropin(c)
+        torch.cuda.empty_cache()
+    if full and world > 1:
+        r4 = run_training(c, "lm", 32, args.steps, args.warmup, pg, graph=not args.no_graph, e2e=True, exposed=True)
+        r4["workload"] = ("configs[3]: batch=%d data-parallel multi-task (DenseBoxLM) training on %dxB200, NCCL grad "
+                          "allreduce(sum) + 1-int positive-count allreduce" % (32 * world, world))
+        c.keep = None
+        torch.cuda.empty_cache()
         barrier()
-    ms = e0.elapsed_time(e1) / args.steps
-    loss_val = float(loss_t.item())
-    # ---- timed: end to end through the public API with HOST (pinned) buffers: every step copies its batch host ->
-    # device and reads its loss back.  The usual prefetching-loader pattern: the copy of batch i+1 is started
-    # (trainer.prefetch, side stream) while step i computes, so it overlaps instead of serialising.
-    def prefetch(b):
-        tr.prefetch(b["x"], b["bbox"], vertices=b.get("vertices"), rand_neg_idx=b["rand"],
-                    lm_rand_neg_idx=b.get("lm_rand"))
-
-    for i in range(2):
-        step(batches[i % nb]).item()
-    barrier()
-    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e2.record()
-    prefetch(batches[0])
-    for i in range(args.steps):
-        loss_h = step(batches[i % nb])        # consumes the staged copy of this batch
-        prefetch(batches[(i + 1) % nb])       # H2D of the next batch, concurrent with this step
-        loss_h.item()                         # D2H read of this step's loss
-    e3.record()
-    barrier()
-    ms_e2e = e2.elapsed_time(e3) / args.steps
-    t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, ms_e2e = float(t[0]), float(t[1])
-    h2d = sum(v.numel() * v.element_size() for v in batches[0].values())
-
-    # ---- per-kernel accounting of one eager step (CUDA events around every launch of the engine)
-    roof, kern = None, None
-    if rank == 0:
-        tr.eng.profile(True)
-        tr._fwd_loss_bwd()
-        tr.eng.sgd_step(tr.lr, tr.momentum, tr.weight_decay)
-        recs = tr.eng.profile_records()
-        tr.eng.profile(False)
-        fam = {}
-        for tag, fl, t_ms in recs:
-            k = tag.split(":")[0]
-            f = fam.setdefault(k, [0.0, 0.0, 0])
-            f[0] += fl; f[1] += t_ms; f[2] += 1
-        tot_ms = sum(f[1] for f in fam.values())
-        kern = {k: {"ms": round(f[1], 4), "share": round(f[1] / tot_ms, 4), "launches": f[2],
-                    "tflops": round(f[0] / f[1] * 1e-9, 1) if f[0] > 0 and f[1] > 0 else None}
-                for k, f in sorted(fam.items(), key=lambda kv: -kv[1][1])}
-        conv = [fam.get("fprop", [0, 0, 0]), fam.get("dgrad", [0, 0, 0])]
-        fl = conv[0][0] + conv[1][0]; tm = conv[0][1] + conv[1][1]
-        ach = fl / tm * 1e-9
-        tp = traffic_from_profile(variant, B)
-        roof = {"kernel": "conv_fprop_kernel + conv3x3_halo_kernel (tcgen05 implicit GEMM: %d fprop + %d dgrad launches per step)"
-                          % (conv[0][2], conv[1][2]),
-                "bound": "tensor", "achieved": round(ach, 1), "peak": pk["tf_sustained"], "unit": "TFLOP/s",
-                "frac": round(ach / pk["tf_sustained"], 4), "traffic": (tp or {}).get("bytes"),
-                "traffic_unit": "DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full)",
-                "traffic_source": (tp or {}).get("source"), "peak_source": pk["source"],
-                "algorithmic_gflop_per_launch_avg": round(fl / max(conv[0][2] + conv[1][2], 1) * 1e-9, 2),
-                "avg_launch_ms": round(tm / max(conv[0][2] + conv[1][2], 1), 4),
-                "step_tflops": round(GFLOP_TRAIN[variant] * B / ms, 1),
-                "step_frac": round(GFLOP_TRAIN[variant] * B / ms / pk["tf_sustained"], 4)}
+        if rank == 0:  # the same variant on ONE GPU of this box (the other ranks wait): base of the LM scaling factor
+            r1 = run_training_single(c, "lm", 32, args.steps, args.warmup, not args.no_graph)
+            r4["single_gpu_same_box"] = r1
+        barrier()
+        records["config4"] = r4
 
     if rank == 0:
-        value = world * B / (ms * 1e-3)
+        if c.sampler is not None:
+            c.sampler.stop()
         line = {
-            "metric": "training patches/sec at 240x240", "value": round(value, 1), "unit": "patches/s",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 4),
+            "metric": METRIC, "value": main_rec["value"], "unit": "patches/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": main_rec["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "configs[1]: batch=32 240x240 bf16 training step, score+bbox heads (DenseBox)"
-                       if variant == "densebox" else "240x240 bf16 training step, %s" % variant,
-                       "variant": variant, "per_gpu_batch": B, "global_batch": B * world,
-                       "parallelism": "dp%d" % world, "step": "fwd + fused loss + bwd + grad allreduce(sum) + SGD",
-                       "cache": "working set %.1f GB per step >> 126 MB L2 (inputs larger than L2, no flush needed)"
-                                % (tr.eng.workspace_bytes / 1e9),
-                       "cuda_graph": not args.no_graph, "weights": "seeded vgg19(weights=None) + xavier heads",
-                       "optimizer": "SGD lr=1e-9 m=0.9 wd=5e-8 (DenseBox.py:2821-2824)"},
-            "e2e": {"value": round(world * B / (ms_e2e * 1e-3), 1), "unit": "patches/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e, 4)},
-            "gpu_launches": int(launches_per_step * args.steps),
-            "gpu_launches_per_step": int(launches_per_step),
-            "clocks": clk.summary(), "roofline": roof, "kernels": kern, "cpu_baseline": cpu_base,
-            "loss": loss_val, "gflop_per_patch": GFLOP_TRAIN[variant],
+            "config": headline_config(world, not args.no_graph) if (variant == "densebox" and B == 32) else
+                      {"workload": "240x240 bf16 training step, %s, per-GPU batch %d (ad-hoc)" % (variant, B),
+                       "variant": variant, "per_gpu_batch": B, "global_batch": B * world, "parallelism": "dp%d" % world},
+            "e2e": main_rec["e2e"],
+            "gpu_launches": int(main_rec["gpu_launches_per_step"] * args.steps),
+            "gpu_launches_per_step": main_rec["gpu_launches_per_step"],
+            "clocks": main_rec["clocks"], "roofline": main_rec.get("roofline"), "kernels": main_rec.get("kernels"),
+            "cpu_baseline": cpu_base, "loss": main_rec["loss"], "gflop_per_patch": GFLOP_TRAIN[variant],
+            "workspace_gb": main_rec["workspace_gb"],
         }
+        if "parity" in main_rec:
+            line["parity"] = main_rec["parity"]
+            line["loss_rel_err"] = main_rec["parity"]["loss_rel_err"]
+        for k in ("exposed_comm_us_per_step", "ms_per_step_without_allreduce"):
+            if k in main_rec:
+                line[k] = main_rec[k]
+        line.update(records)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_training_single(c, variant, B, steps, warmup, graph):
+    """Rank 0 alone: the single-GPU number of `variant` on the same box (no process group)."""
+    c1 = Ctx()
+    c1.dev, c1.rank, c1.world, c1.dist, c1.pk, c1.sampler = c.dev, 0, 1, c.dist, c.pk, None
+    import torch
+    c1.barrier = torch.cuda.synchronize
+    rec = run_training(c1, variant, B, steps, warmup, None, graph=graph, e2e=False)
+    c1.keep = None
+    torch.cuda.empty_cache()
+    return {"value": rec["value"], "unit": "patches/s", "ms_per_step": rec["ms_per_step"]}
 
 
 if __name__ == "__main__":

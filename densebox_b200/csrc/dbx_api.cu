@@ -65,6 +65,27 @@ int dbx_loss_fwd_bwd(const float* head, int HC, const float* rf, int RC, const f
   return loss_fwd_bwd(p, (cudaStream_t)stream);
 }
 
+int dbx_loss_maps(const float* const* maps, const long* strides, float* const* grads, const float* bbox,
+                  const float* vertices, const float* labels, const long long* rand_idx, int rand_stride,
+                  const long long* lm_rand_idx, int variant, float lambda_loc, float lambda_det, float lambda_lm,
+                  int global_pos, int global_batch, const int* global_pos_ptr, int clamp_lm, int B, void* scratch,
+                  float* loss, int* info, unsigned char* mask_out, unsigned char* lm_mask_out, void* stream) {
+  if (!scratch || !maps || !strides) return DBX_ERR_ARG;
+  LossParams p{};
+  for (int g = 0; g < 5; ++g) {
+    p.src[g] = MapRef{maps[g], strides[3 * g], strides[3 * g + 1], strides[3 * g + 2]};
+    p.dst[g] = MapOut{grads ? grads[g] : nullptr, strides[3 * g], strides[3 * g + 1], strides[3 * g + 2]};
+  }
+  p.bbox = bbox; p.vertices = vertices; p.labels = labels;
+  p.rand_idx = rand_idx; p.rand_stride = rand_stride; p.lm_rand_idx = lm_rand_idx; p.variant = variant;
+  p.lambda_loc = lambda_loc; p.lambda_det = lambda_det; p.lambda_lm = lambda_lm;
+  p.global_pos = global_pos; p.global_batch = global_batch; p.global_pos_ptr = global_pos_ptr;
+  p.clamp_lm = clamp_lm; p.B = B;
+  p.counter = (unsigned int*)scratch; p.loss_partial = (float*)scratch + 4;
+  p.loss = loss; p.info = info; p.mask_out = mask_out; p.lm_mask_out = lm_mask_out;
+  return loss_fwd_bwd(p, (cudaStream_t)stream);
+}
+
 int dbx_count_positives(const float* bbox, const float* labels, int B, int* out, void* stream) {
   return count_positives(bbox, labels, B, out, (cudaStream_t)stream);
 }
@@ -119,6 +140,13 @@ int dbx_decode_nms(const float* score, long s_img, long s_pix, const float* loc,
                    float* dets, int* keep, void* stream) {
   return decode_nms(score, s_img, s_pix, loc, l_img, l_pix, l_ch, lmloc, m_img, m_pix, m_ch, N, H4, W4, K, thresh,
                     dets, keep, (cudaStream_t)stream);
+}
+
+int dbx_decode_nms_heat(const float* score, long s_img, long s_pix, const float* loc, long l_img, long l_pix, long l_ch,
+                        const float* lmheat, long m_img, long m_pix, long m_ch, int N, int H4, int W4, int K,
+                        double thresh, float* dets, int* keep, void* stream) {
+  return decode_nms(score, s_img, s_pix, loc, l_img, l_pix, l_ch, lmheat, m_img, m_pix, m_ch, N, H4, W4, K, thresh,
+                    dets, keep, (cudaStream_t)stream, 1);
 }
 
 }  // extern "C"

@@ -40,8 +40,16 @@ Tile choose_tile(int W, int H, int N, bool need_mult16);
 int encode_act_map(CUtensorMap* m, const Act& a, const Tile& t);                // 4D (C, W, H, N), box (64, tw, th, tn)
 int encode_mat_map(CUtensorMap* m, const void* ptr, int rows, int cols, int box_rows); // 2D (cols, rows), box (64, box_rows)
 
-int num_sms();
+int num_sms();          // of the CURRENT device (cached per device)
 bool pdl_enabled();
+// A/B measurement switches (DBX_* environment variables read by the launchers) are honoured only when the process
+// sets DBX_ENABLE_AB=1 before the library is first used; otherwise this returns nullptr for every name, so the kernel
+// selection of a production process cannot be changed through its environment.  INTEGRATION.md lists the switches.
+const char* ab_env(const char* name);
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a per-device setting: applied once per (kernel, device).
+static constexpr int kMaxDevices = 64;
+struct SmemAttrOnce { int done[kMaxDevices]; int rc[kMaxDevices]; };
+int set_max_smem_once(const void* fn, int bytes, SmemAttrOnce* state);
 
 // ---- kernels (launchers). All are asynchronous on `stream`, allocate nothing, and return an error code.
 
@@ -105,6 +113,28 @@ struct TransposeBatch {
 };
 int transpose_dgrad_multi(const void* wk_base, void* wd_base, const TransposeBatch& tb, int total_blocks,
                           cudaStream_t st);
+// Every (weight, bias) pair of a network in ONE launch: mode 0 = torch tensors -> fp32 master + bf16 K-major copies,
+// 1 = flat fp32 buffer (gradients or masters) -> torch tensors.  Entries address the flat buffers by element offset.
+struct ParamXfer {
+  static constexpr int kMax = 24;
+  struct E {
+    float* w; long s_co, s_ci, s_r, s_s;   // torch weight [co,ci,R,S] with element strides
+    float* b; long s_b;                    // torch bias [co]
+    int co, ci, R, S;
+    long long w_off, b_off;                // group matrix / first bias element inside the flat buffers
+    long ld, rowK, kK;                     // K-major placement: row rowK + o, column kK + (r*S+s)*cin_pad + i
+    int cin_pad, dup;                      // dup: conv1_1 pairs layout, second diagonal block (rows 64.., columns 32..)
+    long long elem0;                       // running element count before this entry (weights + biases)
+  } e[kMax];
+  int n;
+  long long total;
+};
+int params_xfer(const ParamXfer& t, int mode, float* flat32, void* flat16, cudaStream_t st);
+// head_out fp32 NHWC [pixels][HC] (+ rf_out [pixels][RC]) <-> the NCHW fp32 tensors the modules return / receive
+int heads_to_nchw(const float* head, int HC, const float* rf, int RC, int N, int HW, float* score, float* loc,
+                  float* lm, float* lmloc, float* rfo, cudaStream_t st);
+int nchw_to_head_grads(const float* g_score, const float* g_loc, const float* g_lm, const float* g_lmloc,
+                       const float* g_rf, int N, int HW, void* d_head, void* d_rf, cudaStream_t st);
 int sgd_step(float* w, float* g, float* v, void* wb, size_t n, float lr, float momentum, float wd, int first,
              int zero_grad, cudaStream_t st);
 int cast_bf16(const float* src, void* dst, size_t n, cudaStream_t st);
@@ -114,9 +144,17 @@ int refine_pool_pack(const float* head, int HC, void* pooled, int N, int H, int 
 int refine_pool_bwd(const float* head, int HC, const void* dpooled, void* dhead, int N, int H, int W, cudaStream_t st);
 
 // ---- fused loss (dbx_loss.cu)
+// One group of fp32 maps with explicit element strides (image, pixel, channel): the engine's NHWC head buffer and the
+// NCHW tensors of the drop-in densebox_loss() are read (and their gradients written) through the same kernel.
+struct MapRef { const float* p; long img, pix, ch; };
+struct MapOut { float* p; long img, pix, ch; };
+enum { LOSS_SCORE = 0, LOSS_LOC = 1, LOSS_LM = 2, LOSS_LMLOC = 3, LOSS_RF = 4 };
 struct LossParams {
   const float* head; int HC;      // [B,60,60,HC] fp32: ch0 score, 1..4 loc, 5..8 landmark heat, 9..16 landmark loc
   const float* rf; int RC;        // [B,60,60,RC] fp32, ch0 = refine score (variants 1,2)
+  MapRef src[5];                  // head == null: the five map groups given one by one (score 1 ch, loc 4, landmark
+                                  // heat 4, landmark loc 8, refine 1); head != null: filled by the launcher
+  MapOut dst[5];                  // optional fp32 gradients per group (p == null: not written)
   const float* bbox;              // [B,4] 60-space
   const float* vertices;          // [B,8] or null
   const float* labels;            // [B] or null (= all positive patches)
@@ -137,7 +175,8 @@ struct LossParams {
   float* d_rf_f32;                // [B,60,60,RC] or null
   unsigned char* mask_out;        // [B,3600] or null
   unsigned char* lm_mask_out;     // [B,4,3600] or null
-  int* info;                      // [2] = {half, pos} or null
+  int* info;                      // [4] = {half, pos, rand_short, 0} or null; rand_short = 1 when half > rand_stride
+                                  // (fewer injected random negatives than the quota asks for)
 };
 int loss_fwd_bwd(const LossParams& p, cudaStream_t st);
 int count_positives(const float* bbox, const float* labels, int B, int* out, cudaStream_t st);
@@ -146,6 +185,6 @@ int count_positives(const float* bbox, const float* labels, int B, int* out, cud
 // ---- detection post-processing (dbx_postproc.cu); maps are fp32 with explicit image/pixel/channel element strides
 int decode_nms(const float* score, long s_img, long s_pix, const float* loc, long l_img, long l_pix, long l_ch,
                const float* lmloc, long m_img, long m_pix, long m_ch, int N, int H4, int W4, int K, double thresh,
-               float* dets, int* keep, cudaStream_t st);
+               float* dets, int* keep, cudaStream_t st, int lm_heat = 0);  // lm_heat: `lmloc` = 4 heat-maps (parse_DetLM)
 
 }  // namespace dbx

@@ -287,9 +287,8 @@ int conv3x3_halo(const Act& x, const void* wk, const Act& out, const ConvEpilogu
   } else {
     tmX = tmO;
   }
-  static int attr_rc = (int)cudaFuncSetAttribute((const void*)conv3x3_halo_kernel,
-                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, kHaloSmem + 1024);
-  if (attr_rc) return attr_rc;
+  static SmemAttrOnce attr_once;
+  { const int arc = set_max_smem_once((const void*)conv3x3_halo_kernel, kHaloSmem + 1024, &attr_once); if (arc) return arc; }
   const int total = p.m_tiles * p.n_tiles;
   const int grid = total < num_sms() ? total : num_sms();
   cudaLaunchConfig_t cfg{};

@@ -461,12 +461,12 @@ __global__ void __launch_bounds__(256) colsum_kernel(Act dy, float* __restrict__
 
 int colsum(const Act& dy, float* db, cudaStream_t st) {
   if (!db || dy.C % 8 || dy.C > 2048) return DBX_ERR_ARG;
-  { const char* e = getenv("DBX_NO_COLSUM"); if (e && e[0] == '1') return DBX_OK; }  // measurement only
+  { const char* e = ab_env("DBX_NO_COLSUM"); if (e && e[0] == '1') return DBX_OK; }  // measurement only
   const int cc = dy.C / 8;
   int rows = 256 / cc; if (rows < 1) rows = 1;
   const size_t pixels = (size_t)dy.N * dy.H * dy.W;
   int blocks = 8 * num_sms();  // measured: fewer, fatter blocks are slower even on the 29 MB layers (latency-bound)
-  { const char* e = getenv("DBX_COLSUM_BLOCKS"); if (e && atoi(e) > 0) blocks = atoi(e) * num_sms(); }
+  { const char* e = ab_env("DBX_COLSUM_BLOCKS"); if (e && atoi(e) > 0) blocks = atoi(e) * num_sms(); }
   if ((size_t)blocks * rows > pixels) blocks = (int)((pixels + rows - 1) / rows);
   if (blocks < 1) blocks = 1;
   const size_t ppb = (pixels + blocks - 1) / blocks;
@@ -585,9 +585,8 @@ int heads2_dgrad(const void* d_head, const void* wd, void* out, size_t pixels, i
   const int threads = tpp * (256 / tpp > 0 ? 256 / tpp : 1);
   if (threads > 256) return DBX_ERR_ARG;
   const size_t smem = (size_t)8 * K * sizeof(float);
-  static int attr_rc = (int)cudaFuncSetAttribute((const void*)heads2_dgrad_kernel,
-                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2048 * 4);
-  if (attr_rc) return attr_rc;
+  static SmemAttrOnce attr_once;
+  { const int arc = set_max_smem_once((const void*)heads2_dgrad_kernel, 8 * 2048 * 4, &attr_once); if (arc) return arc; }
   const int ppb = threads / tpp;
   int blocks = 4 * num_sms();
   if ((size_t)blocks * ppb > pixels) blocks = (int)((pixels + ppb - 1) / ppb);
@@ -647,6 +646,117 @@ int unpack_weights(const float* srcK, long ldK, long rowK, long kK, int cin_pad,
   const size_t total = (size_t)co * ci * R * S;
   unpack_weights_kernel<<<grid_for(total, 256), 256, 0, st>>>(srcK, ldK, rowK, kK, cin_pad, dst, co, ci, R, S, s_co,
                                                               s_ci, s_r, s_s);
+  return (int)cudaGetLastError();
+}
+
+// All parameter tensors of a network in one launch (see ParamXfer): block -> entry by the running element count.
+__global__ void __launch_bounds__(256) params_xfer_kernel(const ParamXfer t, int mode, float* __restrict__ flat32,
+                                                          bf16* __restrict__ flat16) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= t.total) return;
+  int ei = 0;
+#pragma unroll 1
+  while (ei + 1 < t.n && idx >= t.e[ei + 1].elem0) ++ei;
+  const ParamXfer::E& e = t.e[ei];
+  long long l = idx - e.elem0;
+  const long long nw = (long long)e.co * e.ci * e.R * e.S;
+  if (l >= nw) {  // bias
+    const int o = (int)(l - nw);
+    if (o >= e.co) return;
+    if (mode == 0) {
+      const float v = e.b[o * e.s_b];
+      flat32[e.b_off + o] = v;
+      if (e.dup) flat32[e.b_off + 64 + o] = v;
+    } else {
+      e.b[o * e.s_b] = flat32[e.b_off + o];
+    }
+    return;
+  }
+  const int i = (int)(l % e.ci);
+  const int s = (int)((l / e.ci) % e.S);
+  const int r = (int)((l / ((long long)e.ci * e.S)) % e.R);
+  const int o = (int)(l / ((long long)e.ci * e.S * e.R));
+  const long long k = e.w_off + (long long)(e.rowK + o) * e.ld + e.kK + (long long)(r * e.S + s) * e.cin_pad + i;
+  float* tp = e.w + o * e.s_co + i * e.s_ci + r * e.s_r + s * e.s_s;
+  if (mode == 0) {
+    const float v = *tp;
+    flat32[k] = v;
+    flat16[k] = __float2bfloat16_rn(v);
+    if (e.dup) {
+      const long long k2 = k + 64LL * e.ld + 32;
+      flat32[k2] = v;
+      flat16[k2] = __float2bfloat16_rn(v);
+    }
+  } else {
+    *tp = flat32[k];
+  }
+}
+
+int params_xfer(const ParamXfer& t, int mode, float* flat32, void* flat16, cudaStream_t st) {
+  if (t.n < 1 || t.n > ParamXfer::kMax || !flat32 || (mode == 0 && !flat16) || mode < 0 || mode > 1) return DBX_ERR_ARG;
+  params_xfer_kernel<<<grid_for((size_t)t.total, 256), 256, 0, st>>>(t, mode, flat32, (bf16*)flat16);
+  return (int)cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------ head maps <-> NCHW
+// One thread per pixel: reads its HC interleaved floats, writes every channel plane coalesced across the warp.
+__global__ void __launch_bounds__(256) heads_to_nchw_kernel(const float* __restrict__ head, int HC,
+                                                            const float* __restrict__ rf, int RC, int N, int HW,
+                                                            float* __restrict__ score, float* __restrict__ loc,
+                                                            float* __restrict__ lm, float* __restrict__ lmloc,
+                                                            float* __restrict__ rfo) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)N * HW) return;
+  const size_t n = idx / HW, i = idx - n * HW;
+  const float* h = head + idx * HC;
+  if (score) score[idx] = h[0];
+  if (loc) for (int c = 0; c < 4; ++c) loc[(n * 4 + c) * HW + i] = h[1 + c];
+  if (lm) for (int c = 0; c < 4; ++c) lm[(n * 4 + c) * HW + i] = h[5 + c];
+  if (lmloc) for (int c = 0; c < 8; ++c) lmloc[(n * 8 + c) * HW + i] = h[9 + c];
+  if (rfo && rf) rfo[idx] = rf[idx * RC];
+}
+
+int heads_to_nchw(const float* head, int HC, const float* rf, int RC, int N, int HW, float* score, float* loc,
+                  float* lm, float* lmloc, float* rfo, cudaStream_t st) {
+  if (!head || N <= 0 || HW <= 0 || HC < 5 || (lm && HC < 9) || (lmloc && HC < 17) || (rfo && !rf)) return DBX_ERR_ARG;
+  heads_to_nchw_kernel<<<grid_for((size_t)N * HW, 256), 256, 0, st>>>(head, HC, rf, RC, N, HW, score, loc, lm, lmloc,
+                                                                      rfo);
+  return (int)cudaGetLastError();
+}
+
+// The gradients autograd hands to the module's backward (fp32 NCHW, any of them absent) -> the engine's bf16
+// d_head [pixels][64] (channel map of head_out, zero beyond) and d_rf [pixels][64] (channel 0).
+__global__ void __launch_bounds__(256) nchw_to_head_grads_kernel(const float* __restrict__ gs, const float* __restrict__ gl,
+                                                                 const float* __restrict__ gm, const float* __restrict__ gml,
+                                                                 const float* __restrict__ gr, int N, int HW,
+                                                                 bf16* __restrict__ d_head, bf16* __restrict__ d_rf) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)N * HW) return;
+  const size_t n = idx / HW, i = idx - n * HW;
+  float f[24];
+#pragma unroll
+  for (int c = 0; c < 24; ++c) f[c] = 0.f;
+  if (gs) f[0] = gs[idx];
+  if (gl) for (int c = 0; c < 4; ++c) f[1 + c] = gl[(n * 4 + c) * HW + i];
+  if (gm) for (int c = 0; c < 4; ++c) f[5 + c] = gm[(n * 4 + c) * HW + i];
+  if (gml) for (int c = 0; c < 8; ++c) f[9 + c] = gml[(n * 8 + c) * HW + i];
+  uint4* o = reinterpret_cast<uint4*>(d_head + idx * 64);
+  o[0] = pack8(f); o[1] = pack8(f + 8); o[2] = pack8(f + 16);
+#pragma unroll
+  for (int q = 3; q < 8; ++q) o[q] = make_uint4(0u, 0u, 0u, 0u);
+  if (d_rf) {
+    uint4* r = reinterpret_cast<uint4*>(d_rf + idx * 64);
+    r[0] = make_uint4(pack_bf16x2(gr ? gr[idx] : 0.f, 0.f), 0u, 0u, 0u);
+#pragma unroll
+    for (int q = 1; q < 8; ++q) r[q] = make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+
+int nchw_to_head_grads(const float* g_score, const float* g_loc, const float* g_lm, const float* g_lmloc,
+                       const float* g_rf, int N, int HW, void* d_head, void* d_rf, cudaStream_t st) {
+  if (!d_head || N <= 0 || HW <= 0) return DBX_ERR_ARG;
+  nchw_to_head_grads_kernel<<<grid_for((size_t)N * HW, 256), 256, 0, st>>>(g_score, g_loc, g_lm, g_lmloc, g_rf, N, HW,
+                                                                           (bf16*)d_head, (bf16*)d_rf);
   return (int)cudaGetLastError();
 }
 

@@ -30,21 +30,41 @@ static constexpr int kEpiBuf = 16384;           // one epilogue staging buffer: 
 // Programmatic dependent launch of the tensor kernels: opt-in (DBX_PDL=1).  Measured +0.75 % on the sustained step
 // (the prologue of a persistent kernel overlaps the tail of the previous one); all parity tests pass with it, but
 // the gain does not justify making early-scheduled CTAs the default before it has soaked on multi-GPU runs.
+const char* ab_env(const char* name) {
+  static const int enabled = [] { const char* e = getenv("DBX_ENABLE_AB"); return (e && e[0] == '1') ? 1 : 0; }();
+  return enabled ? getenv(name) : nullptr;
+}
+
 bool pdl_enabled() {
   static int v = -1;
-  if (v < 0) { const char* e = getenv("DBX_PDL"); v = (e && e[0] == '1') ? 1 : 0; }
+  if (v < 0) { const char* e = ab_env("DBX_PDL"); v = (e && e[0] == '1') ? 1 : 0; }
   return v == 1;
 }
 
+static int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return (dev >= 0 && dev < kMaxDevices) ? dev : 0;
+}
+
 int num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
+  static int n[kMaxDevices] = {0};
+  const int dev = current_device();
+  if (n[dev] == 0) {
+    int v = 0;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    n[dev] = v > 0 ? v : 148;
   }
-  return n;
+  return n[dev];
+}
+
+int set_max_smem_once(const void* fn, int bytes, SmemAttrOnce* s) {
+  const int dev = current_device();
+  if (!s->done[dev]) {
+    s->rc[dev] = (int)cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    s->done[dev] = 1;
+  }
+  return s->rc[dev];
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -468,10 +488,6 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #undef DBX_TILE_ORIGIN
 }
 
-static int set_max_smem(const void* fn) {
-  cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget + 1024);
-  return (int)e;
-}
 
 int conv_fprop(const Act& x, const void* wk, int R, int S, int pad, const Act& out, const ConvEpilogue& epi,
                int block_n, cudaStream_t stream) {
@@ -484,7 +500,7 @@ int conv_fprop(const Act& x, const void* wk, int R, int S, int pad, const Act& o
   if (epi.aux_mode == 3 && (!epi.rng || epi.rng_channels % 128)) return DBX_ERR_ARG;
   if (R == 3 && S == 3 && pad == 1 && x.C == 64 && out.C == 64 && !epi.out_fp32 && block_n <= 0 &&
       (epi.aux_mode == 1 || epi.aux_mode == 2)) {  // masked epilogue (conv1_2 dgrad); without a mask colbox + CTA pairs wins
-    const char* e = getenv("DBX_HALO");
+    const char* e = ab_env("DBX_HALO");
     if (!(e && e[0] == '0')) {  // 64->64 3x3 layers (conv1_2 fwd/dgrad): column-box kernel, resident filter (A/B: DBX_HALO=0)
       const int rc = conv3x3_halo(x, wk, out, epi, stream);
       if (rc != DBX_ERR_ARG) return rc;
@@ -503,26 +519,26 @@ int conv_fprop(const Act& x, const void* wk, int R, int S, int pad, const Act& o
     const long u256 = m_pairs * ((out.C + 255) / 256), u128 = m_pairs * (out.C / 128);
     const double c256 = (double)((u256 + pairs - 1) / pairs) * 256.0;
     const double c128 = (double)((u128 + pairs - 1) / pairs) * 128.0 * 1.04;
-    const char* e = getenv("DBX_AUTO_BLOCK_N");
+    const char* e = ab_env("DBX_AUTO_BLOCK_N");
     if (c128 < c256 && !(e && e[0] == '0')) block_n = 128;
   }
 
   Tile t = choose_tile(out.W, out.H, out.N, false);
   int tma_epi = epi.out_fp32 ? 0 : 1;
   const bool bf16_out = !epi.out_fp32;
-  { const char* e = getenv("DBX_DIRECT_EPI"); if (e && e[0] == '1' && epi.aux_mode != 3) tma_epi = 0; }  // A/B switch
+  { const char* e = ab_env("DBX_DIRECT_EPI"); if (e && e[0] == '1' && epi.aux_mode != 3) tma_epi = 0; }  // A/B switch
   // Column-box mode (see the kernel) for the 3x3 pad-1 layers on maps that 8 x 16 tiles cover without much waste.
   // Measured (tools/bench_colbox.py, B = 32, generic -> colbox + CTA pairs, TFLOP/s): conv2_1 dgrad 557 -> 1004,
   // conv2_2 975 -> 1322, conv3_1 dgrad 811 -> 1129, conv4_2 1161 -> 1281, conv3_2 1209 -> 1229: the generic mode is
   // bound by barrier round trips (one per 4 MMAs) and TMA delivery on the narrow layers.
   int colbox = 0;
   int colbox_max_n = 256;
-  { const char* e = getenv("DBX_COLBOX_MAX_N"); if (e) colbox_max_n = atoi(e); }
+  { const char* e = ab_env("DBX_COLBOX_MAX_N"); if (e) colbox_max_n = atoi(e); }
   if (R == 3 && S == 3 && pad == 1 && bf16_out && block_n <= colbox_max_n && block_n % 32 == 0 && epi.aux_mode != 3) {
     const double cover = (double)out.W * out.H / ((double)((out.W + 7) / 8 * 8) * ((out.H + 15) / 16 * 16));
     colbox = cover >= 0.87 ? 1 : 0;   // 60 x 60 and 30 x 30 maps: 0.879 (measured: still +30 % on conv3_1 dgrad)
   }
-  { const char* e = getenv("DBX_COLBOX_FPROP"); if (e && R == 3 && S == 3 && pad == 1 && bf16_out) colbox = atoi(e) != 0; }
+  { const char* e = ab_env("DBX_COLBOX_FPROP"); if (e && R == 3 && S == 3 && pad == 1 && bf16_out) colbox = atoi(e) != 0; }
   if (colbox) {
     t.tw = 8; t.th = 16; t.tn = 1;
     t.tiles_w = (out.W + 7) / 8; t.tiles_h = (out.H + 15) / 16; t.tiles_n = out.N;
@@ -531,10 +547,10 @@ int conv_fprop(const Act& x, const void* wk, int R, int S, int pad, const Act& o
   // (measured round 1: +4..6 % on the N = 256 layers once the MMA issue loop was lean; before that the kernel was
   // issue-bound and pairing changed nothing.  ConvEpilogue::force_cta2 = 0 or DBX_CTA2=0 switches it off.)
   int cta2_min_n = colbox ? 64 : 256;
-  { const char* e = getenv("DBX_CTA2_MIN_N"); if (e) cta2_min_n = atoi(e); }
+  { const char* e = ab_env("DBX_CTA2_MIN_N"); if (e) cta2_min_n = atoi(e); }
   const bool cta2_ok = bf16_out && block_n >= cta2_min_n && block_n % 32 == 0 && t.count() >= 2 && num_sms() >= 2;
   int cta2 = (cta2_ok && epi.force_cta2 != 0) ? 1 : 0;
-  { const char* e = getenv("DBX_CTA2"); if (e && cta2_ok) cta2 = e[0] == '1'; }  // A/B switch for measurements
+  { const char* e = ab_env("DBX_CTA2"); if (e && cta2_ok) cta2 = e[0] == '1'; }  // A/B switch for measurements
   CUtensorMap tmA, tmB, tmO, tmX;
   Tile ta = t;
   if (colbox) ta.th = 18;
@@ -574,7 +590,7 @@ int conv_fprop(const Act& x, const void* wk, int R, int S, int pad, const Act& o
   // block) cannot hide -> batch K blocks behind one barrier
   const int b_rows_cta = cta2 ? block_n / 2 : block_n;
   p.kps = b_rows_cta <= 64 ? 2 : 1;  // measured (tools/bench_kps.py): wider tiles lose more to the coarser pipeline
-  { const char* e = getenv("DBX_KPS"); if (e && atoi(e) >= 1 && atoi(e) <= 4) p.kps = atoi(e); }
+  { const char* e = ab_env("DBX_KPS"); if (e && atoi(e) >= 1 && atoi(e) <= 4) p.kps = atoi(e); }
   if (p.kps > R * S * (x.C / 64)) p.kps = R * S * (x.C / 64);
   if (colbox) p.kps = 1;
   p.tma_epi = tma_epi;
@@ -583,7 +599,7 @@ int conv_fprop(const Act& x, const void* wk, int R, int S, int pad, const Act& o
   if (tma_epi && (kSmemBudget - 4 * kEpiBuf) / slot_bytes < 4) p.nbuf = 2;  // keep >= 4 operand K blocks in flight
   if (colbox) p.nbuf = (block_n <= 64 && x.C <= 64) ? 4 : 2;  // measured (tools/bench_colbox.py)
   if (tma_epi && (epi.epi_bufs == 2 || epi.epi_bufs == 4 || epi.epi_bufs == 8)) p.nbuf = epi.epi_bufs;
-  { const char* e = getenv("DBX_EPI_BUFS"); if (e && tma_epi && (atoi(e) == 2 || atoi(e) == 4 || atoi(e) == 8)) p.nbuf = atoi(e); }
+  { const char* e = ab_env("DBX_EPI_BUFS"); if (e && tma_epi && (atoi(e) == 2 || atoi(e) == 4 || atoi(e) == 8)) p.nbuf = atoi(e); }
   p.nbuf_log2 = p.nbuf == 8 ? 3 : (p.nbuf == 4 ? 2 : 1);
   const int ring = tma_epi ? p.nbuf * kEpiBuf : 0;
   while (p.kps > 1 && (kSmemBudget - ring) / (p.kps * slot_bytes) < 2) p.kps >>= 1;
@@ -591,7 +607,7 @@ int conv_fprop(const Act& x, const void* wk, int R, int S, int pad, const Act& o
   const int stage_bytes = p.kps * slot_bytes;
   p.stages = (kSmemBudget - ring) / stage_bytes;
   if (p.stages > kMaxStages) p.stages = kMaxStages;
-  { const char* e = getenv("DBX_STAGES"); if (e && atoi(e) >= 2 && atoi(e) < p.stages) p.stages = atoi(e); }
+  { const char* e = ab_env("DBX_STAGES"); if (e && atoi(e) >= 2 && atoi(e) < p.stages) p.stages = atoi(e); }
   if (p.stages < 2) return DBX_ERR_ARG;
   // fused column sums (bias gradient of the layer below): need 8 x cout floats of spare shared memory behind the ring
   bool colsum_after = false;
@@ -599,7 +615,7 @@ int conv_fprop(const Act& x, const void* wk, int R, int S, int pad, const Act& o
   if (epi.colsum) {
     if (epi.bias) return DBX_ERR_ARG;
     const int used = p.stages * stage_bytes + ring;
-    const char* e = getenv("DBX_FUSED_COLSUM");
+    const char* e = ab_env("DBX_FUSED_COLSUM");
     if (tma_epi && out.C % 2 == 0 && used + 8 * out.C * 4 <= kSmemBudget && !(e && e[0] == '0')) { p.colsum = epi.colsum; p.csum_off = used; }
     else colsum_after = true;   // no room (or fp32 output): same result from the stand-alone kernel after the launch
   }
@@ -615,14 +631,10 @@ int conv_fprop(const Act& x, const void* wk, int R, int S, int pad, const Act& o
   static const FpropFn fns[2][4] = {
       {conv_fprop_kernel<false, 1>, conv_fprop_kernel<false, 2>, conv_fprop_kernel<false, 4>, conv_fprop_kernel<false, 3>},
       {conv_fprop_kernel<true, 1>, conv_fprop_kernel<true, 2>, conv_fprop_kernel<true, 4>, conv_fprop_kernel<true, 3>}};
-  static int attr_rc = [] {
-    int rc = 0;
-    for (int a = 0; a < 2; ++a)
-      for (int b = 0; b < 4; ++b) { const int r = set_max_smem((const void*)fns[a][b]); if (r) rc = r; }
-    return rc;
-  }();
-  if (attr_rc) return attr_rc;
-  const FpropFn fn = fns[cta2 ? 1 : 0][colbox ? 3 : (p.kps == 4 ? 2 : (p.kps == 2 ? 1 : 0))];
+  static SmemAttrOnce attr_once[2][4];
+  const int fa = cta2 ? 1 : 0, fb = colbox ? 3 : (p.kps == 4 ? 2 : (p.kps == 2 ? 1 : 0));
+  const FpropFn fn = fns[fa][fb];
+  { const int arc = set_max_smem_once((const void*)fn, kSmemBudget + 1024, &attr_once[fa][fb]); if (arc) return arc; }
   const size_t smem = (size_t)p.stages * stage_bytes + ring + (p.colsum ? (size_t)8 * out.C * 4 : 0) + 1024;
   cudaLaunchConfig_t cfg{};
   cfg.blockDim = dim3(kFpropThreads);
@@ -857,7 +869,7 @@ int conv_wgrad(const Act& x, const Act& dy, int R, int S, int pad, float* dw, in
   // Measured (tools/bench_wgrad.py, TFLOP/s, generic -> column box): conv2_2 932 -> 1294, conv3_1 876 -> 1173; from
   // Cin = 256 up the CTA-pair path with 4 input boxes per stage wins (conv3_2 1426 vs 1287, conv4_2 1445 vs 917).
   int colbox = (R == 3 && S == 3 && pad == 1 && x.C <= 128 && block_n_in <= 0) ? 1 : 0;
-  { const char* e = getenv("DBX_COLBOX");
+  { const char* e = ab_env("DBX_COLBOX");
     if (e && e[0] == '0') colbox = 0;
     if (e && e[0] == '1' && R == 3 && S == 3 && pad == 1 && block_n_in <= 0) colbox = 1; }
   CUtensorMap tmDy, tmX;
@@ -889,7 +901,7 @@ int conv_wgrad(const Act& x, const Act& dy, int R, int S, int pad, float* dw, in
   p.boxes_total = t.count();
   // CTA pairs (cta_group::2) share the shifted-input boxes: worth it from two output-channel tiles up
   int cta2 = (!colbox && p.m_tiles >= 2 && block_n == 256 && num_sms() >= 2) ? 1 : 0;
-  { const char* e = getenv("DBX_CTA2"); if (e && e[0] == '0') cta2 = 0; }
+  { const char* e = ab_env("DBX_CTA2"); if (e && e[0] == '0') cta2 = 0; }
   const int m_units = cta2 ? (p.m_tiles + 1) / 2 : p.m_tiles;
   const int tiles = m_units * p.q_tiles;
   const int workers = cta2 ? num_sms() / 2 : num_sms();
@@ -909,9 +921,10 @@ int conv_wgrad(const Act& x, const Act& dy, int R, int S, int pad, float* dw, in
   p.idesc = umma_idesc_bf16(cta2 ? 256 : 128, block_n, 1, 1);
   p.tmem_cols = tmem_cols_for(2 * block_n);
 
-  static int attr_rc1 = set_max_smem((const void*)conv_wgrad_kernel<false>);
-  static int attr_rc2 = set_max_smem((const void*)conv_wgrad_kernel<true>);
-  if (attr_rc1 || attr_rc2) return attr_rc1 ? attr_rc1 : attr_rc2;
+  static SmemAttrOnce attr_once[2];
+  { const int arc = set_max_smem_once(cta2 ? (const void*)conv_wgrad_kernel<true> : (const void*)conv_wgrad_kernel<false>,
+                                      kSmemBudget + 1024, &attr_once[cta2 ? 1 : 0]);
+    if (arc) return arc; }
   const int total = tiles * p.splits;
   const size_t smem = (size_t)p.stages * stage_bytes + 1024;
   cudaLaunchConfig_t cfg{};

@@ -165,6 +165,13 @@ __device__ void top1_mark(const uint32_t* keys, unsigned char* sel, uint32_t* ws
   __syncthreads();
 }
 
+__device__ __forceinline__ float ldm(const MapRef& m, int b, int i, int c) {
+  return m.p[(size_t)b * m.img + (size_t)i * m.pix + (size_t)c * m.ch];
+}
+__device__ __forceinline__ void stm(const MapOut& m, int b, int i, int c, float v) {
+  m.p[(size_t)b * m.img + (size_t)i * m.pix + (size_t)c * m.ch] = v;
+}
+
 __global__ void __launch_bounds__(LT) loss_kernel(const LossParams p) {
   __shared__ uint32_t keys[MAPN];
   __shared__ unsigned char mask[MAPN];
@@ -197,17 +204,19 @@ __global__ void __launch_bounds__(LT) loss_kernel(const LossParams p) {
   const int gbatch = p.global_batch > 0 ? p.global_batch : p.B;
   const int neg_num = (int)((double)pos / (double)gbatch + 0.5);
   const int half = (int)((double)neg_num * 0.5 + 0.5);
-  if (b == 0 && tid == 0 && p.info) { p.info[0] = half; p.info[1] = pos; }
+  if (b == 0 && tid == 0 && p.info) {
+    p.info[0] = half; p.info[1] = pos;
+    p.info[2] = (p.rand_idx && half > p.rand_stride) ? 1 : 0;  // the caller gave fewer random negatives than the quota
+  }
 
   Box sbox = clip(0, 0, 0, 0), gout = sbox, gin = sbox;
   if (positive) { sbox = score_box(bb); gray_boxes(bb, gout, gin); }
 
   // ---- classification mask: positives + hard negatives + random negatives, then gray zone
-  const float* head = p.head + (size_t)b * MAPN * p.HC;
   for (int i = tid; i < MAPN; i += LT) {
     const int y = i / MAPW, x = i - y * MAPW;
     const bool g = positive && inbox(sbox, x, y);
-    const float s = head[(size_t)i * p.HC];
+    const float s = ldm(p.src[LOSS_SCORE], b, i, 0);
     const float d = s - (g ? 1.f : 0.f);
     keys[i] = g ? 0u : __float_as_uint(d * d);  // (s-gt)^2 * (1-gt) >= 0
     mask[i] = g ? 1 : 0;
@@ -249,7 +258,7 @@ __global__ void __launch_bounds__(LT) loss_kernel(const LossParams p) {
       for (int i = tid; i < MAPN; i += LT) {
         const int y = i / MAPW, x = i - y * MAPW;
         const bool g = (x == px && y == py);
-        const float d = head[(size_t)i * p.HC + 5 + k] - (g ? 1.f : 0.f);
+        const float d = ldm(p.src[LOSS_LM], b, i, k) - (g ? 1.f : 0.f);
         keys[i] = g ? 0u : __float_as_uint(d * d);
         lmm[k][i] = g ? 1 : 0;
       }
@@ -280,11 +289,10 @@ __global__ void __launch_bounds__(LT) loss_kernel(const LossParams p) {
     const int y = i / MAPW, x = i - y * MAPW;
     const float m = (float)mask[i];
     const float g = (positive && inbox(sbox, x, y)) ? 1.f : 0.f;
-    const float* h = head + (size_t)i * p.HC;
     float dh[17];
 #pragma unroll
     for (int c = 0; c < 17; ++c) dh[c] = 0.f;
-    float t = h[0] - g;
+    float t = ldm(p.src[LOSS_SCORE], b, i, 0) - g;
     float part = m * t * t;                      // cls
     dh[0] = 2.f * ldet * m * t;
     const float mg = m * g;
@@ -294,7 +302,7 @@ __global__ void __launch_bounds__(LT) loss_kernel(const LossParams p) {
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         const float gtc = positive ? gt[c] : 0.f;
-        t = h[1 + c] - gtc;
+        t = ldm(p.src[LOSS_LOC], b, i, c) - gtc;
         loc_part += mg * t * t;
         dh[1 + c] = 2.f * ldet * p.lambda_loc * mg * t;
       }
@@ -306,7 +314,7 @@ __global__ void __launch_bounds__(LT) loss_kernel(const LossParams p) {
       for (int k = 0; k < 4; ++k) {
         const float mk = (float)lmm[k][i];
         const float gk = (x == lmx[k] && y == lmy[k]) ? 1.f : 0.f;
-        t = h[5 + k] - gk;
+        t = ldm(p.src[LOSS_LM], b, i, k) - gk;
         lm_part += mk * t * t;
         dh[5 + k] = 2.f * p.lambda_lm * mk * t;
       }
@@ -317,13 +325,13 @@ __global__ void __launch_bounds__(LT) loss_kernel(const LossParams p) {
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           const float gtc = positive ? (((c & 1) ? (float)y : (float)x) - v[c]) : 0.f;
-          t = h[9 + c] - gtc;
+          t = ldm(p.src[LOSS_LMLOC], b, i, c) - gtc;
           ll += mg * t * t;
           dh[9 + c] = 2.f * mg * t;
         }
         li += (double)ll;
       }
-      const float r = p.rf[((size_t)b * MAPN + i) * p.RC];
+      const float r = ldm(p.src[LOSS_RF], b, i, 0);
       t = r - g;
       li += (double)(m * t * t);
       const float dr = 2.f * m * t;
@@ -334,6 +342,7 @@ __global__ void __launch_bounds__(LT) loss_kernel(const LossParams p) {
         for (int q = 1; q < 8; ++q) o[q] = make_uint4(0u, 0u, 0u, 0u);
       }
       if (p.d_rf_f32) p.d_rf_f32[((size_t)b * MAPN + i) * p.RC] = dr;
+      if (p.dst[LOSS_RF].p) stm(p.dst[LOSS_RF], b, i, 0, dr);
     }
     acc += li;
     if (p.d_head) {
@@ -349,6 +358,19 @@ __global__ void __launch_bounds__(LT) loss_kernel(const LossParams p) {
     if (p.d_head_f32) {
       float* o = p.d_head_f32 + ((size_t)b * MAPN + i) * p.HC;
       for (int c = 0; c < p.HC; ++c) o[c] = c < 17 ? dh[c] : 0.f;
+    }
+    if (p.dst[LOSS_SCORE].p) stm(p.dst[LOSS_SCORE], b, i, 0, dh[0]);
+    if (p.dst[LOSS_LOC].p) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) stm(p.dst[LOSS_LOC], b, i, c, dh[1 + c]);
+    }
+    if (p.dst[LOSS_LM].p) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) stm(p.dst[LOSS_LM], b, i, c, dh[5 + c]);
+    }
+    if (p.dst[LOSS_LMLOC].p) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) stm(p.dst[LOSS_LMLOC], b, i, c, dh[9 + c]);
     }
     if (p.mask_out) p.mask_out[(size_t)b * MAPN + i] = mask[i];
     if (p.lm_mask_out && has_lm)
@@ -389,11 +411,22 @@ int count_positives(const float* bbox, const float* labels, int B, int* out, cud
   return (int)cudaGetLastError();
 }
 
-int loss_fwd_bwd(const LossParams& p, cudaStream_t st) {
-  if (!p.head || !p.bbox || !p.loss_partial || !p.loss || !p.counter || p.B <= 0) return DBX_ERR_ARG;
+int loss_fwd_bwd(const LossParams& pin, cudaStream_t st) {
+  LossParams p = pin;
+  if (!p.bbox || !p.loss_partial || !p.loss || !p.counter || p.B <= 0) return DBX_ERR_ARG;
   if (p.variant < 0 || p.variant > 2) return DBX_ERR_ARG;
-  if (p.HC < (p.variant == 2 ? 17 : (p.variant == 1 ? 9 : 5))) return DBX_ERR_ARG;
-  if (p.variant >= 1 && (!p.rf || !p.vertices || p.RC < 1)) return DBX_ERR_ARG;
+  if (p.head) {  // one interleaved NHWC buffer (the engine's head_out / rf_out): derive the five groups
+    if (p.HC < (p.variant == 2 ? 17 : (p.variant == 1 ? 9 : 5))) return DBX_ERR_ARG;
+    if (p.variant >= 1 && (!p.rf || p.RC < 1)) return DBX_ERR_ARG;
+    const int first[4] = {0, 1, 5, 9};
+    for (int g = 0; g < 4; ++g) p.src[g] = MapRef{p.head + first[g], (long)MAPN * p.HC, (long)p.HC, 1L};
+    p.src[LOSS_RF] = MapRef{p.rf, (long)MAPN * p.RC, (long)p.RC, 1L};
+  } else {
+    if (p.d_head_f32 || p.d_rf_f32) return DBX_ERR_ARG;  // the interleaved fp32 gradients belong to the NHWC form
+  }
+  if (!p.src[LOSS_SCORE].p || !p.src[LOSS_LOC].p) return DBX_ERR_ARG;
+  if (p.variant >= 1 && (!p.src[LOSS_LM].p || !p.src[LOSS_RF].p || !p.vertices)) return DBX_ERR_ARG;
+  if (p.variant == 2 && !p.src[LOSS_LMLOC].p) return DBX_ERR_ARG;
   loss_kernel<<<p.B, LT, 0, st>>>(p);
   return (int)cudaGetLastError();
 }

@@ -54,6 +54,7 @@ struct Net {
   char* ws = nullptr;
   size_t ws_bytes = 0;
   size_t flat_n = 0;     // fp32 elements in the flat parameter buffer (weights then biases)
+  size_t tail_off = 0, bias_off = 0;  // first element of the conv1..conv3 filters / of the biases (see build())
   size_t wd_n = 0;       // bf16 elements in the dgrad-layout buffer
   bool forward_done = false, loss_done = false;
   int sgd_steps = 0;
@@ -121,7 +122,7 @@ struct Net {
 
   void build(int variant_, int N_, int H_, int W_, int train_) {
     variant = variant_; N = N_; H = H_; W = W_; train = train_;
-    { const char* e = getenv("DBX_CONV1_PAIRS"); pairs = !(e && e[0] == '0') && (W % 2 == 0); }
+    { const char* e = ab_env("DBX_CONV1_PAIRS"); pairs = !(e && e[0] == '0') && (W % 2 == 0); }
     nh = variant == 0 ? 2 : (variant == 1 ? 3 : 4);
     HC = variant == 2 ? 32 : 16;
     const int starts[5] = {0, 1, 5, 9, 17};
@@ -145,8 +146,15 @@ struct Net {
       add_group("conv6_2_det", 64, 25, 64, true);
       add_group("conv6_3_det", 16, 1, 64, true);
     }
+    // Flat parameter order: the filters whose gradients are complete after backward stage 0 (conv4_1 .. heads,
+    // refine) come FIRST, then conv1_1 .. conv3_4, then every bias: gradient bucket 0 = [0, tail_off) can be
+    // all-reduced under stage 1 and everything that stage 1 finishes is ONE contiguous tail [tail_off, flat_n).
     size_t off = 0, wd = 0;
-    for (auto& g : groups) { g.w_off = off; off += align_up((size_t)g.rows * g.ld, 64); }
+    const size_t g4 = (size_t)group_id("conv4_1");
+    for (size_t i = g4; i < groups.size(); ++i) { groups[i].w_off = off; off += align_up((size_t)groups[i].rows * groups[i].ld, 64); }
+    tail_off = off;
+    for (size_t i = 0; i < g4; ++i) { groups[i].w_off = off; off += align_up((size_t)groups[i].rows * groups[i].ld, 64); }
+    bias_off = off;
     for (auto& g : groups) { g.b_off = off; off += align_up((size_t)g.rows, 64); }
     flat_n = off;
     for (auto& g : groups)
@@ -277,6 +285,51 @@ struct Net {
     }
     return unpack_weights(base + g.w_off, g.ld, p.rowK, p.kK, p.cin_pad, dst, p.cout, p.cin, p.R, p.S, s_co, s_ci,
                           s_r, s_s, st);
+  }
+  // every listed (weight, bias) pair in one launch: mode 0 = torch -> w32 + wk, 1 = w32 -> torch, 2 = g32 -> torch
+  int xfer_params(int mode, int n, const char* const* names, void* const* w_ptrs, const long* w_strides,
+                  void* const* b_ptrs, const long* b_strides, cudaStream_t st) {
+    if (mode < 0 || mode > 2 || n < 1 || n > ParamXfer::kMax || !names || !w_ptrs || !w_strides || !b_ptrs || !b_strides)
+      return DBX_ERR_ARG;
+    if (mode == 2 && !train) return DBX_ERR_STATE;
+    ParamXfer t{};
+    long long elems = 0;
+    for (int k = 0; k < n; ++k) {
+      const int id = names[k] ? param_id(names[k]) : -1;
+      if (id < 0 || !w_ptrs[k] || !b_ptrs[k]) return DBX_ERR_ARG;
+      const Param& p = params[id];
+      const Group& g = groups[p.grp];
+      ParamXfer::E& e = t.e[k];
+      e.w = (float*)w_ptrs[k]; e.s_co = w_strides[4 * k]; e.s_ci = w_strides[4 * k + 1];
+      e.s_r = w_strides[4 * k + 2]; e.s_s = w_strides[4 * k + 3];
+      e.b = (float*)b_ptrs[k]; e.s_b = b_strides[k];
+      e.co = p.cout; e.ci = p.cin; e.R = p.R; e.S = p.S;
+      e.w_off = (long long)g.w_off; e.b_off = (long long)g.b_off + p.rowK;
+      e.ld = g.ld; e.rowK = p.rowK; e.kK = p.kK; e.cin_pad = p.cin_pad;
+      e.dup = (pairs && p.name == "conv1_1") ? 1 : 0;
+      e.elem0 = elems;
+      elems += (long long)p.cout * p.cin * p.R * p.S + p.cout;
+    }
+    t.n = n; t.total = elems;
+    DBX_K("params_xfer", 0.0, params_xfer(t, mode == 0 ? 0 : 1, mode == 2 ? G32() : W32(), WK(), st));
+    return DBX_OK;
+  }
+  // head maps as the NCHW fp32 tensors the reference modules return (any pointer may be null)
+  int get_outputs(float* score, float* loc, float* lm, float* lmloc, float* rf, cudaStream_t st) {
+    if (!forward_done) return DBX_ERR_STATE;
+    if ((lm && variant < 1) || (rf && variant < 1) || (lmloc && variant < 2)) return DBX_ERR_ARG;
+    DBX_K("heads_to_nchw", 0.0, heads_to_nchw((const float*)buf("head_out"), HC, variant >= 1 ? (const float*)buf("rf_out") : nullptr,
+                                              16, N, (H / 4) * (W / 4), score, loc, lm, lmloc, rf, st));
+    return DBX_OK;
+  }
+  // d(loss)/d(outputs) as autograd delivers them (fp32 NCHW, null = zero) -> "d_head" / "d_rf"
+  int set_output_grads(const float* g_score, const float* g_loc, const float* g_lm, const float* g_lmloc,
+                       const float* g_rf, cudaStream_t st) {
+    if (!train) return DBX_ERR_STATE;
+    if ((g_lm && variant < 1) || (g_rf && variant < 1) || (g_lmloc && variant < 2)) return DBX_ERR_ARG;
+    DBX_K("nchw_to_head_grads", 0.0, nchw_to_head_grads(g_score, g_loc, g_lm, g_lmloc, g_rf, N, (H / 4) * (W / 4), buf("d_head"),
+                                                        variant >= 1 ? buf("d_rf") : nullptr, st));
+    return DBX_OK;
   }
   // bf16 dgrad-layout copies of every filter (call after the weights changed, before backward)
   bool dgrad_stale = false;   // set by sgd(): the flipped filters are rebuilt on the side stream during forward
@@ -460,14 +513,14 @@ struct Net {
     if (dgrad_stale) DBX_TRY(refresh_dgrad(st));
     // bias gradients come out of the epilogue of the launch that produces dZ (DBX_FUSE_BIAS=0: stand-alone colsum)
     bool fuse = true;
-    { const char* e = getenv("DBX_FUSE_BIAS"); if (e && e[0] == '0') fuse = false; }
+    { const char* e = ab_env("DBX_FUSE_BIAS"); if (e && e[0] == '0') fuse = false; }
     bool pool_idx = true;
-    { const char* e = getenv("DBX_POOL_IDX"); if (e && e[0] == '0') pool_idx = false; }
+    { const char* e = ab_env("DBX_POOL_IDX"); if (e && e[0] == '0') pool_idx = false; }
     // The two short-K data gradients (conv2_2, conv1_2) are paced by their epilogue: the column sums cost them
     // +0.047 / +0.05 ms (measured, with or without shared-memory atomics) against 0.027 / 0.05 ms for the stand-alone
     // pass on the side stream, so their bias gradients stay with wgrad().  DBX_FUSE_BIAS_SHORT=1 fuses them too.
     bool fuse_short = false;
-    { const char* e = getenv("DBX_FUSE_BIAS_SHORT"); if (e && e[0] == '1') fuse_short = fuse; }
+    { const char* e = ab_env("DBX_FUSE_BIAS_SHORT"); if (e && e[0] == '1') fuse_short = fuse; }
     const int h2 = H / 2, w2 = W / 2, h4 = H / 4, w4 = W / 4, h8 = H / 8, w8 = W / 8;
     Act col0 = act("col0", H, W, 64), a11 = act("a11", H, W, 64), a12 = act("a12", H, W, 64);
     Act p1 = act("p1", h2, w2, 64), a21 = act("a21", h2, w2, 128), a22 = act("a22", h2, w2, 128);
@@ -512,7 +565,7 @@ struct Net {
       // independent implementation for parity (tests/test_gpu_fused_bias.py); measured 0.18 ms against 0.115 ms —
       // Philox + dropout + bias fold per element make it instruction-bound — so it is not the default.
       bool direct = false;
-      { const char* e = getenv("DBX_HEADS2_DGRAD"); if (e && e[0] == '1') direct = true; }
+      { const char* e = ab_env("DBX_HEADS2_DGRAD"); if (e && e[0] == '1') direct = true; }
       if (direct) {
         heads1_bias_done = fuse;
         DBX_K("dgrad:heads2", 2.0 * pixels(d_head64) * macs_of("heads2"),
@@ -677,6 +730,20 @@ int dbx_net_get_grad(void* handle, const char* name, int is_bias, float* dst, lo
   if (!handle) return DBX_ERR_ARG;
   return ((Net*)handle)->get_tensor(name, is_bias, 1, dst, s_co, s_ci, s_r, s_s, (cudaStream_t)stream);
 }
+int dbx_net_xfer_params(void* handle, int mode, int n, const char* const* names, void* const* w_ptrs,
+                        const long* w_strides, void* const* b_ptrs, const long* b_strides, void* stream) {
+  if (!handle) return DBX_ERR_ARG;
+  return ((Net*)handle)->xfer_params(mode, n, names, w_ptrs, w_strides, b_ptrs, b_strides, (cudaStream_t)stream);
+}
+int dbx_net_get_outputs(void* handle, float* score, float* loc, float* lm, float* lmloc, float* rf, void* stream) {
+  if (!handle) return DBX_ERR_ARG;
+  return ((Net*)handle)->get_outputs(score, loc, lm, lmloc, rf, (cudaStream_t)stream);
+}
+int dbx_net_set_output_grads(void* handle, const float* g_score, const float* g_loc, const float* g_lm,
+                             const float* g_lmloc, const float* g_rf, void* stream) {
+  if (!handle) return DBX_ERR_ARG;
+  return ((Net*)handle)->set_output_grads(g_score, g_loc, g_lm, g_lmloc, g_rf, (cudaStream_t)stream);
+}
 int dbx_net_refresh_dgrad(void* handle, void* stream) {
   if (!handle) return DBX_ERR_ARG;
   return ((Net*)handle)->refresh_dgrad((cudaStream_t)stream);
@@ -717,12 +784,12 @@ int dbx_net_grad_bucket(void* handle, int bucket, long long* first, long long* c
   if (!handle || !first || !count) return DBX_ERR_ARG;
   Net* n = (Net*)handle;
   if (!n->train) return DBX_ERR_STATE;
-  const long long split = (long long)n->groups[n->group_id("conv4_1")].w_off;
-  const long long bias0 = (long long)n->groups[0].b_off;
+  const long long split = (long long)n->tail_off, bias0 = (long long)n->bias_off;
   switch (bucket) {
-    case 0: *first = split; *count = bias0 - split; return DBX_OK;            // conv4_1 .. heads (+ refine) filters
-    case 1: *first = 0; *count = split; return DBX_OK;                         // conv1_1 .. conv3_4 filters
+    case 0: *first = 0; *count = split; return DBX_OK;                         // conv4_1 .. heads (+ refine) filters
+    case 1: *first = split; *count = bias0 - split; return DBX_OK;             // conv1_1 .. conv3_4 filters
     case 2: *first = bias0; *count = (long long)n->flat_n - bias0; return DBX_OK;  // every bias
+    case 3: *first = split; *count = (long long)n->flat_n - split; return DBX_OK;  // 1 + 2: all that stage 1 completes
     default: return DBX_ERR_ARG;
   }
 }

@@ -1,5 +1,6 @@
 // densebox_b200 — detection post-processing, one CTA per image: top-K of the raw score map, box / landmark decode
-// and greedy NMS (reference: parse_out_MN / parse_DetLMLOC DenseBox.py:3114-3217, NMS :3398-3443).
+// and greedy NMS (reference: parse_out_MN / parse_DetLMLOC DenseBox.py:3114-3217, parse_DetLM :3220-3300 — landmarks =
+// the arg-max of each landmark heat-map, the same four points for every detection of the image —, NMS :3398-3443).
 // The reference does this on the CPU after five D2H copies per image; here only K rows leave the GPU.
 #include "dbx_common.h"
 #include "dbx_ptx.cuh"
@@ -13,7 +14,9 @@ __device__ __forceinline__ float mv(const MapView& m, int n, int idx, int c) {
   return __ldg(m.p + (size_t)n * m.img + (size_t)idx * m.pix + (size_t)c * m.ch);
 }
 
-__global__ void __launch_bounds__(PT) decode_nms_kernel(MapView score, MapView loc, MapView lmloc, int has_lm, int HW,
+// lm_mode: 0 = boxes only, 1 = `lm` holds 8 landmark offsets per pixel (parse_DetLMLOC), 2 = `lm` holds 4 landmark
+// heat-maps whose arg-max (lowest index among equals) gives the landmark (parse_DetLM :3283-3292).
+__global__ void __launch_bounds__(PT) decode_nms_kernel(MapView score, MapView loc, MapView lmloc, int lm_mode, int HW,
                                                         int W4, int K, double thresh, float* __restrict__ dets,
                                                         int* __restrict__ keep) {
   __shared__ float wv[PT / 32];
@@ -22,10 +25,36 @@ __global__ void __launch_bounds__(PT) decode_nms_kernel(MapView score, MapView l
   __shared__ float selv[KMAX];
   __shared__ double box[KMAX][4];
   __shared__ int alive[KMAX];
+  __shared__ int lmarg[4];
   const int n = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int KS = K;  // row stride of the outputs
+  const int has_lm = lm_mode == 1;
   if (K > KMAX) K = KMAX;
   if (K > HW) K = HW;
+  if (lm_mode == 2) {  // per-landmark arg-max of the heat-maps (torch.topk(k=1) of :3285)
+    for (int k = 0; k < 4; ++k) {
+      float bv = -INFINITY; int bi = 0x7fffffff;
+      for (int i = tid; i < HW; i += PT) {
+        const float v = mv(lmloc, n, i, k);
+        if (v > bv || bi == 0x7fffffff) { bv = v; bi = i; }  // ascending i: the first maximum stays
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (oi != 0x7fffffff && (bi == 0x7fffffff || ov > bv || (ov == bv && oi < bi))) { bv = ov; bi = oi; }
+      }
+      if (lane == 0) { wv[warp] = bv; wi[warp] = bi; }
+      __syncthreads();
+      if (tid == 0) {
+        float v = wv[0]; int i = wi[0];
+        for (int w = 1; w < PT / 32; ++w)
+          if (wi[w] != 0x7fffffff && (i == 0x7fffffff || wv[w] > v || (wv[w] == v && wi[w] < i))) { v = wv[w]; i = wi[w]; }
+        lmarg[k] = i;
+      }
+      __syncthreads();
+    }
+  }
   // ---- top-K by K rounds of block arg-max (ties: lowest index); torch.topk(sorted) order = descending score
   for (int k = 0; k < K; ++k) {
     float bv = -INFINITY; int bi = 0x7fffffff;
@@ -59,8 +88,12 @@ __global__ void __launch_bounds__(PT) decode_nms_kernel(MapView score, MapView l
     float b[4];
     for (int c = 0; c < 4; ++c) b[c] = __fsub_rn((float)((c & 1) ? yi : xi), mv(loc, n, idx, c)) * 4.0f;
     d[0] = b[0]; d[1] = b[1]; d[2] = b[2]; d[3] = b[3]; d[4] = selv[tid];
-    for (int c = 0; c < 8; ++c)
-      d[5 + c] = has_lm ? __fsub_rn((float)((c & 1) ? yi : xi), mv(lmloc, n, idx, c)) * 4.0f : 0.f;
+    for (int c = 0; c < 8; ++c) {
+      float v = 0.f;
+      if (has_lm) v = __fsub_rn((float)((c & 1) ? yi : xi), mv(lmloc, n, idx, c)) * 4.0f;
+      else if (lm_mode == 2) v = (float)((c & 1) ? lmarg[c >> 1] / W4 : lmarg[c >> 1] % W4) * 4.0f;
+      d[5 + c] = v;
+    }
     for (int c = 0; c < 4; ++c) box[tid][c] = (double)b[c];
     alive[tid] = 1;
   }
@@ -87,10 +120,11 @@ __global__ void __launch_bounds__(PT) decode_nms_kernel(MapView score, MapView l
 
 int decode_nms(const float* score, long s_img, long s_pix, const float* loc, long l_img, long l_pix, long l_ch,
                const float* lmloc, long m_img, long m_pix, long m_ch, int N, int H4, int W4, int K, double thresh,
-               float* dets, int* keep, cudaStream_t st) {
+               float* dets, int* keep, cudaStream_t st, int lm_heat) {
   if (!score || !loc || !dets || !keep || N <= 0 || K <= 0 || K > KMAX) return DBX_ERR_ARG;
+  if (lm_heat && !lmloc) return DBX_ERR_ARG;
   MapView s{score, s_img, s_pix, 0}, l{loc, l_img, l_pix, l_ch}, m{lmloc ? lmloc : loc, m_img, m_pix, m_ch};
-  decode_nms_kernel<<<N, PT, 0, st>>>(s, l, m, lmloc ? 1 : 0, H4 * W4, W4, K, thresh, dets, keep);
+  decode_nms_kernel<<<N, PT, 0, st>>>(s, l, m, lmloc ? (lm_heat ? 2 : 1) : 0, H4 * W4, W4, K, thresh, dets, keep);
   return (int)cudaGetLastError();
 }
 

@@ -51,7 +51,9 @@ class NetEngine:
         self.h = h
         self.HC = L.dbx_net_head_channels(self.h)
         self.h4, self.w4 = H // 4, W // 4
-        self._keep = []
+        self.generation = 0        # bumped by every forward(): autograd nodes check that their activations are live
+        self._param_key = None     # identity + version of the module parameters last packed (modules._sync_params)
+        self._dgrad_fresh = False  # the flipped/transposed filter copies match the current weights
 
     def __del__(self):
         try:
@@ -82,8 +84,13 @@ class NetEngine:
         return self.scalars()[0]
 
     def loss_info(self):
-        i = self.buffer("scalars", torch.int32)
-        return int(i[2]), int(i[3])
+        """(half, pos) of the last loss launch; raises if fewer random negatives were supplied than the quota needs
+        (the reference draws `half` of them per sample, DenseBox.py:2888-2893).  Synchronises."""
+        i = self.buffer("scalars", torch.int32)[2:5].tolist()
+        if i[2]:
+            raise DbxError("densebox loss: the negative quota half=%d exceeds the %s random negatives per sample that "
+                           "were supplied" % (i[0], "rand_neg_idx"))
+        return i[0], i[1]
 
     # ---- parameters
     @staticmethod
@@ -110,8 +117,78 @@ class NetEngine:
         check(fn(self.h, name.encode(), c_int(1), ptr(b), *self._strides(b), stream_ptr()), "get(%s.bias)" % name)
         return w, b
 
+    def dropout_stride(self):
+        """Philox counters one forward consumes (one call covers 128 elements of the dropped activation)."""
+        nh = len(HEAD_NAMES[self.variant])
+        return (self.N * self.h4 * self.w4 * 512 * nh + 127) // 128
+
     def refresh_dgrad(self):
         check(lib().dbx_net_refresh_dgrad(self.h, stream_ptr()), "refresh_dgrad")
+        self._dgrad_fresh = True
+
+    # ---- all parameters of a module in one launch (dbx_net_xfer_params)
+    def _xfer(self, mode, triples, what):
+        n = len(triples)
+        names = (ctypes.c_char_p * n)(*[t[0].encode() for t in triples])
+        wp = (ctypes.c_void_p * n)(*[t[1].data_ptr() for t in triples])
+        bp = (ctypes.c_void_p * n)(*[t[2].data_ptr() for t in triples])
+        ws = (ctypes.c_long * (4 * n))()
+        bs = (ctypes.c_long * n)()
+        for i, (_, w, b) in enumerate(triples):
+            assert w.dtype == torch.float32 and b.dtype == torch.float32 and w.is_cuda and b.is_cuda
+            st = list(w.stride()) + [0, 0, 0]
+            ws[4 * i:4 * i + 4] = st[:4]
+            bs[i] = b.stride(0)
+        check(lib().dbx_net_xfer_params(self.h, c_int(mode), c_int(n), names, wp, ws, bp, bs, stream_ptr()), what)
+
+    def set_params(self, module, device=None):
+        """Pack every (weight, bias) the variant uses from a drop-in module (or any object with `_wb(name)`)."""
+        dev = self.device if device is None else device
+        triples = []
+        for name in unique_param_names(self.variant):
+            w, b = module._wb(name)
+            triples.append((name, w.detach().to(dev), b.detach().to(dev)))
+        self._xfer(0, triples, "xfer_params(set)")
+        self._dgrad_fresh = False
+
+    def get_params(self, module):
+        """Write the engine's fp32 master weights back into the module's parameters (in place)."""
+        triples = []
+        for name in unique_param_names(self.variant):
+            w, b = module._wb(name)
+            triples.append((name, w.detach(), b.detach()))
+        self._xfer(1, triples, "xfer_params(get)")
+        if hasattr(module, "_param_epoch"):
+            module._param_epoch += 1  # raw in-place writes do not bump torch's version counters
+
+    def get_grads(self, module):
+        """Fresh fp32 tensors shaped like the module's parameters holding the engine's gradients: [w0, b0, w1, ...]."""
+        triples, out = [], []
+        for name in unique_param_names(self.variant):
+            w, b = module._wb(name)
+            gw = torch.empty_like(w, memory_format=torch.contiguous_format)
+            gb = torch.empty_like(b)
+            triples.append((name, gw, gb))
+            out += [gw, gb]
+        self._xfer(2, triples, "xfer_params(grads)")
+        return out
+
+    def get_outputs(self, want):
+        """NCHW fp32 copies of the head maps: want = subset of ('score','loc','lm','lmloc','rf') -> dict."""
+        ch = {"score": 1, "loc": 4, "lm": 4, "lmloc": 8, "rf": 1}
+        out = {k: torch.empty(self.N, ch[k], self.h4, self.w4, device=self.device) for k in want}
+        check(lib().dbx_net_get_outputs(self.h, *[ptr(out.get(k)) for k in ("score", "loc", "lm", "lmloc", "rf")],
+                                        stream_ptr()), "net_get_outputs")
+        return out
+
+    def set_output_grads(self, grads):
+        """grads: dict name -> fp32 NCHW tensor or None (zero); fills the bf16 d_head / d_rf regions."""
+        g = {}
+        for k in ("score", "loc", "lm", "lmloc", "rf"):
+            t = grads.get(k)
+            g[k] = t.float().contiguous() if t is not None else None
+        check(lib().dbx_net_set_output_grads(self.h, *[ptr(g[k]) for k in ("score", "loc", "lm", "lmloc", "rf")],
+                                             stream_ptr()), "net_set_output_grads")
 
     # ---- the path
     def forward(self, x, dropout_mode=0, seed=0, offset=0):
@@ -119,6 +196,7 @@ class NetEngine:
         assert tuple(x.shape) == (self.N, 3, self.H, self.W), (tuple(x.shape), (self.N, 3, self.H, self.W))
         check(lib().dbx_net_forward(self.h, ptr(x), c_int(dropout_mode), c_ull(seed), c_ull(offset), stream_ptr()),
               "net_forward")
+        self.generation += 1
 
     def loss(self, bbox, vertices=None, labels=None, rand_idx=None, lm_rand_idx=None, lambda_loc=3.0, lambda_det=1.0,
              lambda_lm=0.5, global_pos=-1, global_batch=-1, global_pos_dev=None, clamp_lm=False, d_head_f32=None,
@@ -143,8 +221,13 @@ class NetEngine:
     def join(self):
         check(lib().dbx_net_join(self.h, stream_ptr()), "net_join")
 
+    def grad_tail(self):
+        """conv1..conv3 filters + every bias: what backward stage 1 completes, one contiguous range."""
+        return self.grad_bucket(3)
+
     def grad_bucket(self, bucket):
-        """View of g32 holding gradient bucket 0 (conv4..heads filters), 1 (conv1..conv3 filters) or 2 (biases)."""
+        """View of g32 holding gradient bucket 0 (conv4..heads filters), 1 (conv1..conv3 filters), 2 (biases) or
+        3 (= 1 + 2, contiguous)."""
         first, count = ctypes.c_longlong(0), ctypes.c_longlong(0)
         check(lib().dbx_net_grad_bucket(self.h, c_int(bucket), ctypes.byref(first), ctypes.byref(count)),
               "net_grad_bucket")

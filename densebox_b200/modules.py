@@ -20,44 +20,60 @@ _HEAD_CH = {"det": 1, "loc": 4, "landmark": 4, "lmloc": 8}
 
 
 class _NativeForward(torch.autograd.Function):
-    """forward = engine.forward, backward = engine.backward; parameters are listed so autograd routes their grads."""
+    """forward = engine.forward, backward = engine.backward; parameters are listed so autograd routes their grads.
+
+    The engine keeps ONE set of activations per module: a backward pass is only valid for the most recent forward.
+    Every forward stamps a generation on the engine; `backward` raises if another forward has overwritten the
+    activations in between (e.g. `o1 = net(a); o2 = net(b); (L(o1) + L(o2)).backward()`), instead of silently
+    returning the gradients of the wrong batch.  No gradient is produced for the input X (the reference's loops never
+    ask for one): an X with requires_grad=True is rejected."""
 
     @staticmethod
     def forward(ctx, module, eng, x, *params):
-        module._sync_params(eng)
-        mode = 0
-        if module.training:
-            if module.dropout_mask is not None:  # parity tests inject the oracle's {0,2} masks
-                module._inject_dropout(eng)
-                mode = 2
-            else:
-                mode = 1
-        seed = int(torch.randint(0, 2 ** 31 - 1, (1,)).item()) if mode == 1 else 0
-        eng.forward(x.contiguous(), dropout_mode=mode, seed=seed)
-        outs = module._outputs(eng)
-        ctx.module, ctx.eng = module, eng
+        with torch.cuda.device(x.device):
+            module._sync_params(eng)
+            mode, seed, offset = 0, 0, 0
+            if module.training:
+                if module.dropout_mask is not None:  # parity tests inject the oracle's {0,2} masks
+                    module._inject_dropout(eng)
+                    mode = 2
+                else:  # Philox inside the conv epilogues: stream = torch's seed + this module, counter = call number
+                    mode = 1
+                    seed = (torch.initial_seed() + 0x9E3779B97F4A7C15 * module._instance) & 0x7FFFFFFFFFFFFFFF
+                    offset = module._drop_calls * eng.dropout_stride()
+                    module._drop_calls += 1
+            eng.forward(x.contiguous(), dropout_mode=mode, seed=seed, offset=offset)
+            outs = module._outputs(eng)
+        ctx.module, ctx.eng, ctx.generation = module, eng, eng.generation
         return outs
 
     @staticmethod
     def backward(ctx, *gouts):
         module, eng = ctx.module, ctx.eng
-        module._pack_output_grads(eng, gouts)
-        eng.refresh_dgrad()
-        eng.zero_grad()
-        eng.backward()
-        grads = []
-        for name in unique_param_names(module.variant):
-            w, b = module._wb(name)
-            gw, gb = eng.get_tensor(name, w, b, grad=True)
-            grads += [gw, gb]
+        if ctx.generation != eng.generation:
+            raise RuntimeError(
+                "densebox_b200: backward() of a forward whose activations were overwritten by a later forward of the "
+                "same module (one workspace per module: call backward before the next forward)")
+        with torch.cuda.device(eng.device):
+            eng.set_output_grads(dict(zip(module._out_keys, gouts)))
+            if not eng._dgrad_fresh:
+                eng.refresh_dgrad()
+            eng.zero_grad()
+            eng.backward()
+            grads = eng.get_grads(module)
         return (None, None, None) + tuple(grads)
 
 
 class _DenseBoxBase(nn.Module):
     variant = "densebox"
+    _instances = 0
 
     def __init__(self, vgg19):
         super().__init__()
+        _DenseBoxBase._instances += 1
+        self._instance = _DenseBoxBase._instances  # separates the dropout streams of two modules under one torch seed
+        self._drop_calls = 0
+        self._param_epoch = 0                      # bumped by writers that bypass torch's version counters
         feats = vgg19.features._modules
         for name, idx in _VGG_BLOCKS:  # each block twice: `<name>_1`/`<name>_2` and the Sequential `<name>`
             conv = copy.deepcopy(feats[str(idx)])
@@ -108,9 +124,16 @@ class _DenseBoxBase(nn.Module):
         return eng
 
     def _sync_params(self, eng):
+        """Re-pack the weights into the engine only when a parameter changed since the last forward (optimizer steps,
+        load_state_dict and .data assignments all change the (data_ptr, version) key): ONE launch for all tensors."""
+        key = [self._param_epoch]
         for name in unique_param_names(self.variant):
             w, b = self._wb(name)
-            eng.set_param(name, w, b)
+            key += [w.data_ptr(), w._version, b.data_ptr(), b._version]
+        key = tuple(key)
+        if eng._param_key != key:
+            eng.set_params(self)
+            eng._param_key = key
 
     def _inject_dropout(self, eng):
         nh = len(HEAD_NAMES[eng.variant])
@@ -119,30 +142,14 @@ class _DenseBoxBase(nn.Module):
             m = self.dropout_mask[h].to(drop.device)
             drop[..., 512 * i:512 * (i + 1)] = m.permute(0, 2, 3, 1).to(torch.bfloat16)
 
-    def _maps(self, eng):
-        ho = eng.head_out()
-        pick = lambda a, b: ho[..., a:b].permute(0, 3, 1, 2).contiguous()
-        return {"score": pick(0, 1), "loc": pick(1, 5), "lm": pick(5, 9), "lmloc": pick(9, 17),
-                "rf": eng.rf_out()[..., 0:1].permute(0, 3, 1, 2).contiguous() if eng.variant >= 1 else None}
-
-    def _pack_output_grads(self, eng, gouts):
-        g = dict(zip(self._out_keys, gouts))
-        dh = eng.buffer("d_head", torch.bfloat16, (eng.N, eng.h4, eng.w4, 64))
-        dh.zero_()
-        for key, (a, b) in {"score": (0, 1), "loc": (1, 5), "lm": (5, 9), "lmloc": (9, 17)}.items():
-            if g.get(key) is not None:
-                dh[..., a:b] = g[key].permute(0, 2, 3, 1).to(torch.bfloat16)
-        if eng.variant >= 1:
-            dr = eng.buffer("d_rf", torch.bfloat16, (eng.N, eng.h4, eng.w4, 64))
-            dr.zero_()
-            if g.get("rf") is not None:
-                dr[..., 0:1] = g["rf"].permute(0, 2, 3, 1).to(torch.bfloat16)
-
     def _outputs(self, eng):
-        m = self._maps(eng)
+        m = eng.get_outputs(self._out_keys)  # fresh NCHW fp32 tensors, one launch
         return tuple(m[k] for k in self._out_keys)
 
     def forward(self, X):
+        if X.requires_grad:
+            raise ValueError("densebox_b200: no gradient is produced for the input X (DenseBox.py's loops never ask "
+                             "for one); pass X.detach()")
         params = []
         for name in unique_param_names(self.variant):
             params += list(self._wb(name))

@@ -2,8 +2,13 @@
 step: H2D of the batch, forward, fused loss, hand-written backward, gradient all-reduce (data parallel), SGD.
 
 The reference's loop crosses the host/device boundary 7+ times per step and synchronises twice; here nothing leaves
-the GPU between the input copy and the scalar loss.  With `use_cuda_graph=True` forward+loss+backward and the SGD
-update are replayed as CUDA graphs.
+the GPU between the input copy and the scalar loss, and the host never has to wait for the device:
+  * the batch lives in one of TWO input slots; `prefetch()` copies the next host batch into the idle slot on a side
+    stream while the current step computes, and each slot has its own captured CUDA graph (forward + loss + backward +
+    SGD in ONE graph launch) that reads the slot in place — no per-step restaging copy;
+  * the loss of every step lands in a ring of device scalars (the tensor `step()` returns stays valid for
+    `LOSS_RING` further steps) and, with `async_loss=True`, in a pinned host word behind an event, so a training
+    loop can log the loss of step i while step i+1 is already queued (`PendingLoss.item()`).
 Data parallel: one process per GPU, batch sharded by rank, gradient SUM all-reduce (the loss is a sum,
 DenseBox.py:2917), and the negative quota uses the batch-GLOBAL positive count (:2864-2868) via a 1-int all-reduce.
 Both exchanges are hidden behind compute: the count all-reduce runs while the forward graph replays (only the loss
@@ -18,12 +23,30 @@ from ._lib import check, lib, ptr, stream_ptr
 from .engine import NetEngine, unique_param_names
 
 c_int = ctypes.c_int
+LOSS_RING = 256
+
+
+class PendingLoss:
+    """The loss of one step, read back without stalling the launch of the next one: `tensor` is the device scalar,
+    `item()` waits for the 4-byte device-to-host copy that was queued right behind the step."""
+
+    __slots__ = ("tensor", "_host", "_event")
+
+    def __init__(self, tensor, host, event):
+        self.tensor, self._host, self._event = tensor, host, event
+
+    def item(self):
+        self._event.synchronize()
+        return float(self._host)
+
+    def __float__(self):
+        return self.item()
 
 
 class DenseBoxTrainer:
     def __init__(self, net, batch_size, lr=1e-9, momentum=0.9, weight_decay=5e-8, lambda_loc=3.0, lambda_det=1.0,
                  lambda_lm=0.5, patch=240, rand_width=256, process_group=None, use_cuda_graph=True, dropout=True,
-                 device=None, seed=0):
+                 device=None, seed=0, allreduce_loss=False):
         self.net = net
         self.variant = net.variant
         self.B = batch_size
@@ -31,208 +54,251 @@ class DenseBoxTrainer:
         self.lambdas = (lambda_loc, lambda_det, lambda_lm)
         self.pg = process_group
         self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
+        self.rank = torch.distributed.get_rank(process_group) if process_group is not None else 0
+        self.allreduce_loss = bool(allreduce_loss) and self.world > 1
         self.dropout = dropout
-        self.seed, self.step_no = seed, 0
+        # independent dropout streams per rank (the reference's nn.Dropout draws per process): fold the rank in
+        self.seed = (seed ^ (self.rank * 0x9E3779B97F4A7C15)) & 0x7FFFFFFFFFFFFFFF if self.world > 1 else seed
+        self.step_no = 0
         self.device = torch.device(device if device is not None else torch.cuda.current_device())
         self.eng = NetEngine(self.variant, batch_size, patch, patch, train=True, device=self.device)
         dev = self.device
-        self.x = torch.zeros(batch_size, 3, patch, patch, device=dev)
-        self.bbox = torch.zeros(batch_size, 4, device=dev)
-        self.vertices = torch.zeros(batch_size, 8, device=dev)
-        self.labels = torch.ones(batch_size, device=dev)
-        self.rand = torch.zeros(batch_size, rand_width, dtype=torch.int64, device=dev)
-        self.lm_rand = torch.zeros(batch_size, 4, dtype=torch.int64, device=dev)
-        self.gpos = torch.zeros(1, dtype=torch.int32, device=dev)
-        self.use_labels = False
+        with torch.cuda.device(dev):
+            self.slots = [self._new_slot(batch_size, patch, rand_width, dev) for _ in range(2)]
+            self.gpos = torch.zeros(1, dtype=torch.int32, device=dev)
+            self._loss_ring = torch.zeros(LOSS_RING, device=dev)
+            self._loss_host = torch.zeros(LOSS_RING, pin_memory=True)
+            self._loss_events = [None] * LOSS_RING
         self.use_graph = use_cuda_graph
-        self._graph_fb = self._graph_sgd = None
-        self._graphs_dp = None  # (forward, loss + backward stage 0, backward stage 1) when world > 1
-        self._graph_lr = None
+        self._graphs = {}          # capture key -> CUDAGraph (single GPU: whole step) / tuple of 3 (data parallel)
+        self._graph_sgd = {}       # lr -> CUDAGraph of the SGD update (data parallel: it follows the all-reduce)
+        self._skip_allreduce = False   # measurement aid (bench.py: exposed-communication time); never set in training
         self._rng = self.eng.buffer("rng", torch.int64)
         drop_elems = self.eng.buffer("drop", torch.bfloat16).numel()
         self._rng_stride = (drop_elems + 127) // 128  # Philox calls consumed by one step
         # {seed, offset}: the offset advances by one stride per step INSIDE the captured step (device side, no
         # per-step host write); it starts one stride before 0 so that step n draws from offset n * stride
-        self._rng[0] = seed
+        self._rng[0] = self.seed
         self._rng[1] = -self._rng_stride
         self._rng_off = self._rng[1:2]
-        # prefetch(): host batch i+1 is copied on a side stream into staging buffers while step i computes
-        self._pf = None            # {"x": ..., "bbox": ..., ...} staging tensors (lazily allocated)
-        self._pf_key = None        # identity of the host tensors staged last
+        # input slots: `_cur` is the slot the next step() uses; prefetch() fills it on the copy stream
+        self._cur = 0
+        self._staged = None        # (identity key of the host tensors, slot) of the last prefetch()
         self._pf_stream = None
-        self._pf_ready = None      # event: staging complete (recorded on the copy stream)
-        self._pf_free = None       # event: staging buffers consumed (recorded on the compute stream)
+        self._slot_ready = [None, None]   # events: H2D into the slot complete (copy stream)
+        self._slot_free = [None, None]    # events: the step that read the slot has finished (compute stream)
         self.load_from_module()
+
+    @staticmethod
+    def _new_slot(B, patch, rand_width, dev):
+        return {"x": torch.zeros(B, 3, patch, patch, device=dev), "bbox": torch.zeros(B, 4, device=dev),
+                "vertices": torch.zeros(B, 8, device=dev), "labels": torch.ones(B, device=dev),
+                "rand": torch.zeros(B, rand_width, dtype=torch.int64, device=dev),
+                "lm_rand": torch.zeros(B, 4, dtype=torch.int64, device=dev), "labels_are_ones": True}
 
     # ---- parameters
     def load_from_module(self):
-        for name in unique_param_names(self.variant):
-            w, b = self.net._wb(name)
-            self.eng.set_param(name, w.detach().to(self.device), b.detach().to(self.device))
-        self.eng.refresh_dgrad()
-        self.eng.zero_grad()
+        with torch.cuda.device(self.device):
+            self.eng.set_params(self.net, device=self.device)
+            self.eng.refresh_dgrad()
+            self.eng.zero_grad()
 
     @torch.no_grad()
     def store_to_module(self):
-        for name in unique_param_names(self.variant):
-            w, b = self.net._wb(name)
-            gw, gb = self.eng.get_tensor(name, w, b, grad=False)
-            w.copy_(gw)
-            b.copy_(gb)
+        with torch.cuda.device(self.device):
+            self.eng.get_params(self.net)
 
-    # ---- one step
-    def _stage(self, dst, src):
-        if src is None or src is dst:
-            return
-        src = torch.as_tensor(src)
-        dst.copy_(src.reshape(dst.shape) if src.numel() == dst.numel() else src, non_blocking=True)
-
+    # ---- input staging
     @staticmethod
     def _key(*tensors):
         return tuple((t.data_ptr(), tuple(t.shape)) if torch.is_tensor(t) else None for t in tensors)
 
+    def _fill_slot(self, k, x, bbox, vertices, labels, rand_neg_idx, lm_rand_neg_idx):
+        """Copy one batch into slot k on the CURRENT stream (host tensors: asynchronous when pinned)."""
+        s = self.slots[k]
+
+        def put(dst, src):
+            src = torch.as_tensor(src)
+            dst.copy_(src.reshape(dst.shape) if src.numel() == dst.numel() else src, non_blocking=True)
+
+        put(s["x"], x)
+        put(s["bbox"], bbox)
+        if vertices is not None:
+            put(s["vertices"], vertices)
+        if labels is not None:
+            put(s["labels"], labels)
+            s["labels_are_ones"] = False
+        elif not s["labels_are_ones"]:
+            s["labels"].fill_(1.0)
+            s["labels_are_ones"] = True
+        if rand_neg_idx is None:
+            s["rand"].copy_(torch.rand(self.B, 3600, device=self.device).argsort(dim=1)[:, :s["rand"].shape[1]])
+        else:
+            r = torch.as_tensor(rand_neg_idx)
+            w = min(r.shape[1], s["rand"].shape[1])
+            if w == s["rand"].shape[1] and r.shape[1] == w:
+                s["rand"].copy_(r, non_blocking=True)
+            else:
+                s["rand"][:, :w].copy_(r[:, :w], non_blocking=True)
+        if self.variant != "densebox":
+            if lm_rand_neg_idx is None:
+                s["lm_rand"].copy_(torch.randint(0, 3600, (self.B, 4), device=self.device))
+            else:
+                put(s["lm_rand"], lm_rand_neg_idx)
+
     def prefetch(self, x, bbox, vertices=None, labels=None, rand_neg_idx=None, lm_rand_neg_idx=None):
-        """Start the host->device copy of the NEXT batch (pinned host tensors) on a side stream; a following
-        `step()` called with the same tensors finds them in device staging buffers and only pays a device-to-device
-        copy.  The usual prefetching-loader pattern: `step(batch_i)`, `prefetch(batch_i+1)`, then read the loss.
-        The staged copy is matched by tensor identity (data pointer + shape): do not modify the host tensors between
+        """Start the host->device copy of the NEXT batch (pinned host tensors) on a side stream, straight into the
+        input slot the next `step()` will read; that `step()`, called with the same tensors, copies nothing.  The
+        usual prefetching-loader pattern: `step(batch_i)`, `prefetch(batch_i+1)`, then read the loss.  The staged
+        copy is matched by tensor identity (data pointer + shape): do not modify the host tensors between
         `prefetch()` and the `step()` that consumes them."""
-        args = {"x": x, "bbox": bbox, "vertices": vertices, "labels": labels, "rand": rand_neg_idx,
-                "lm_rand": lm_rand_neg_idx}
-        if not all(v is None or (torch.is_tensor(v) and not v.is_cuda) for v in args.values()):
+        args = (x, bbox, vertices, labels, rand_neg_idx, lm_rand_neg_idx)
+        if not all(v is None or (torch.is_tensor(v) and not v.is_cuda) for v in args):
             return  # device tensors or non-tensors: nothing to overlap, step() handles them
-        if self._pf is None:
-            self._pf = {"x": torch.empty_like(self.x), "bbox": torch.empty_like(self.bbox),
-                        "vertices": torch.empty_like(self.vertices), "labels": torch.empty_like(self.labels),
-                        "rand": torch.empty_like(self.rand), "lm_rand": torch.empty_like(self.lm_rand)}
-            self._pf_stream = torch.cuda.Stream(device=self.device)
-            self._pf_ready = torch.cuda.Event()
-            self._pf_free = torch.cuda.Event()
-            self._pf_free.record(torch.cuda.current_stream(self.device))
-        with torch.cuda.stream(self._pf_stream):
-            self._pf_stream.wait_event(self._pf_free)  # the previous staged batch has been consumed
-            for k, v in args.items():
-                if v is None:
-                    continue
-                dst = self._pf[k]
-                if k == "rand":
-                    dst[:, :v.shape[1]].copy_(v[:, :dst.shape[1]], non_blocking=True)
-                else:
-                    dst.copy_(v.reshape(dst.shape) if v.numel() == dst.numel() else v, non_blocking=True)
-            self._pf_ready.record(self._pf_stream)
-        self._pf_key = self._key(x, bbox, vertices, labels, rand_neg_idx, lm_rand_neg_idx)
+        if rand_neg_idx is None or (self.variant != "densebox" and lm_rand_neg_idx is None):
+            return  # device-side draws happen in step()
+        k = self._cur
+        with torch.cuda.device(self.device):
+            if self._pf_stream is None:
+                self._pf_stream = torch.cuda.Stream(device=self.device)
+            with torch.cuda.stream(self._pf_stream):
+                if self._slot_free[k] is not None:
+                    self._pf_stream.wait_event(self._slot_free[k])  # the step that last read this slot is done
+                self._fill_slot(k, *args)
+                if self._slot_ready[k] is None:
+                    self._slot_ready[k] = torch.cuda.Event()
+                self._slot_ready[k].record(self._pf_stream)
+        self._staged = (self._key(*args), k)
 
-    def _take_prefetched(self, x, bbox, vertices, labels, rand_neg_idx, lm_rand_neg_idx):
-        """If exactly these host tensors were staged by prefetch(): substitute the staging buffers (device)."""
-        if self._pf_key is None or self._pf_key != self._key(x, bbox, vertices, labels, rand_neg_idx, lm_rand_neg_idx):
-            return x, bbox, vertices, labels, rand_neg_idx, lm_rand_neg_idx, False
-        self._pf_key = None
-        torch.cuda.current_stream(self.device).wait_event(self._pf_ready)
-        pf = self._pf
-        return (pf["x"], pf["bbox"], pf["vertices"] if vertices is not None else None,
-                pf["labels"] if labels is not None else None,
-                pf["rand"][:, :rand_neg_idx.shape[1]] if rand_neg_idx is not None else None,
-                pf["lm_rand"] if lm_rand_neg_idx is not None else None, True)
+    # ---- the step
+    def _loss(self, s, clamp_lm):
+        ll, ld, lm = self.lambdas
+        self.eng.loss(s["bbox"], vertices=s["vertices"] if self.variant != "densebox" else None, labels=s["labels"],
+                      rand_idx=s["rand"], lm_rand_idx=s["lm_rand"] if self.variant != "densebox" else None,
+                      lambda_loc=ll, lambda_det=ld, lambda_lm=lm, global_pos_dev=self.gpos if self.world > 1 else None,
+                      global_batch=self.B * self.world if self.world > 1 else -1, clamp_lm=clamp_lm)
 
-    def _fwd_loss_bwd(self):
-        e = self.eng
+    def _forward(self, s):
         if self.dropout:
             self._rng_off.add_(self._rng_stride)  # a fresh dropout mask per step (captured with the step)
-        e.forward(self.x, dropout_mode=3 if self.dropout else 0)  # Philox in the epilogues, state in the rng region
-        self._loss()
-        e.backward()
+        self.eng.forward(s["x"], dropout_mode=3 if self.dropout else 0)  # Philox in the epilogues, state in `rng`
 
-    def _loss(self):
-        ll, ld, lm = self.lambdas
-        self.eng.loss(self.bbox, vertices=self.vertices if self.variant != "densebox" else None,
-                      labels=self.labels if self.use_labels else None, rand_idx=self.rand,
-                      lm_rand_idx=self.lm_rand if self.variant != "densebox" else None, lambda_loc=ll, lambda_det=ld,
-                      lambda_lm=lm, global_pos_dev=self.gpos if self.world > 1 else None,
-                      global_batch=self.B * self.world if self.world > 1 else -1, clamp_lm=self.use_labels)
+    def _fwd_loss_bwd(self, s=None, clamp_lm=False):
+        s = s if s is not None else self.slots[self._cur]
+        self._forward(s)
+        self._loss(s, clamp_lm)
+        self.eng.backward()
 
-    def _step_dp(self, graph_ok):
+    def _step_single(self, k, clamp_lm, graph_ok):
+        s = self.slots[k]
+        if not graph_ok:
+            self._fwd_loss_bwd(s, clamp_lm)
+            self.eng.sgd_step(self.lr, self.momentum, self.weight_decay)
+            return
+        key = (k, clamp_lm, self.lr)
+        g = self._graphs.get(key)
+        if g is None:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._fwd_loss_bwd(s, clamp_lm)
+                self.eng.sgd_step(self.lr, self.momentum, self.weight_decay)
+            self._graphs[key] = g  # capture does not execute: fall through to the replay
+        g.replay()
+
+    def _step_dp(self, k, clamp_lm, graph_ok):
         """forward | loss + backward(heads, conv4) | backward(conv3..conv1) with the two exchanges overlapped."""
-        e, dist = self.eng, torch.distributed
+        e, dist, s = self.eng, torch.distributed, self.slots[k]
 
         def fwd():
-            if self.dropout:
-                self._rng_off.add_(self._rng_stride)
-            e.forward(self.x, dropout_mode=3 if self.dropout else 0)
+            self._forward(s)
             e.join()
 
         def lb0():
-            self._loss()
+            self._loss(s, clamp_lm)
             e.backward_stage(0)
 
         parts = (fwd, lb0, lambda: e.backward_stage(1))
-        if graph_ok and self._graphs_dp is None:  # capture before any collective of this step is in flight
-            self._graphs_dp = []
+        key = (k, clamp_lm)
+        if graph_ok and key not in self._graphs:  # capture before any collective of this step is in flight
+            gs = []
             for fn in parts:
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g, capture_error_mode="thread_local"):
                     fn()
-                self._graphs_dp.append(g)
-        check(lib().dbx_count_positives(ptr(self.bbox), ptr(self.labels if self.use_labels else None),
-                                        c_int(self.B), ptr(self.gpos), stream_ptr()), "count_positives")
-        w_count = dist.all_reduce(self.gpos, group=self.pg, async_op=True)
-        run = [g.replay for g in self._graphs_dp] if graph_ok else parts
+                gs.append(g)
+            self._graphs[key] = tuple(gs)
+        check(lib().dbx_count_positives(ptr(s["bbox"]), ptr(s["labels"]), c_int(self.B), ptr(self.gpos), stream_ptr()),
+              "count_positives")
+        comm = not self._skip_allreduce
+        w_count = dist.all_reduce(self.gpos, group=self.pg, async_op=True) if comm else None
+        run = [g.replay for g in self._graphs[key]] if graph_ok else parts
         run[0]()
-        w_count.wait()
+        if w_count is not None:
+            w_count.wait()
         run[1]()
-        works = [dist.all_reduce(e.grad_bucket(0), group=self.pg, async_op=True)]  # SUM: the loss is a sum (:2917)
+        works = []
+        if comm:
+            works.append(dist.all_reduce(e.grad_bucket(0), group=self.pg, async_op=True))  # SUM: the loss is a sum (:2917)
         run[2]()
-        works += [dist.all_reduce(e.grad_bucket(b), group=self.pg, async_op=True) for b in (1, 2)]
+        if comm:
+            works.append(dist.all_reduce(e.grad_tail(), group=self.pg, async_op=True))  # conv1..conv3 filters + biases
         for w in works:
             w.wait()
-
-    def step(self, x, bbox, vertices=None, labels=None, rand_neg_idx=None, lm_rand_neg_idx=None):
-        """x [B,3,240,240] fp32 (host pinned or device), labels in 60-space. Returns the loss as a 0-dim CUDA tensor
-        (this rank's shard; call .item() to read it back)."""
-        e = self.eng
-        x, bbox, vertices, labels, rand_neg_idx, lm_rand_neg_idx, staged = self._take_prefetched(
-            x, bbox, vertices, labels, rand_neg_idx, lm_rand_neg_idx)
-        self._stage(self.x, x)
-        self._stage(self.bbox, bbox)
-        self._stage(self.vertices, vertices)
-        if labels is not None:
-            self._stage(self.labels, labels)
-            self.use_labels = True
-        if rand_neg_idx is None:
-            self.rand.copy_(torch.rand(self.B, 3600, device=self.device).argsort(dim=1)[:, :self.rand.shape[1]])
-        else:
-            r = torch.as_tensor(rand_neg_idx)
-            self.rand[:, :r.shape[1]].copy_(r[:, :self.rand.shape[1]], non_blocking=True)
-        if self.variant != "densebox":
-            if lm_rand_neg_idx is None:
-                self.lm_rand.copy_(torch.randint(0, 3600, (self.B, 4), device=self.device))
-            else:
-                self._stage(self.lm_rand, lm_rand_neg_idx)
-        if staged:  # the staging buffers may be refilled once these device-to-device copies are done
-            self._pf_free.record(torch.cuda.current_stream(self.device))
-        graph_ok = self.use_graph and self.step_no >= 1  # step 0 runs eagerly (one-time inits, SGD first-step flag)
-        if self.world > 1:
-            self._step_dp(graph_ok)
-        else:
-            if graph_ok and self._graph_fb is None:
-                self._graph_fb = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(self._graph_fb):
-                    self._fwd_loss_bwd()
-            if graph_ok:
-                self._graph_fb.replay()
-            else:
-                self._fwd_loss_bwd()
-        if graph_ok and (self._graph_sgd is None or self._graph_lr != self.lr):
-            self._graph_sgd = torch.cuda.CUDAGraph()
-            self._graph_lr = self.lr
-            with torch.cuda.graph(self._graph_sgd, capture_error_mode="thread_local"):
-                e.sgd_step(self.lr, self.momentum, self.weight_decay)
-            # capture does not execute: fall through to replay
         if graph_ok:
-            self._graph_sgd.replay()
+            g = self._graph_sgd.get(self.lr)
+            if g is None:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                    e.sgd_step(self.lr, self.momentum, self.weight_decay)
+                self._graph_sgd[self.lr] = g
+            g.replay()
         else:
             e.sgd_step(self.lr, self.momentum, self.weight_decay)
-        self.step_no += 1
-        return e.loss_value()
+
+    def step(self, x, bbox, vertices=None, labels=None, rand_neg_idx=None, lm_rand_neg_idx=None, async_loss=False):
+        """x [B,3,240,240] fp32 (host pinned or device), labels in 60-space.  Returns the loss of this rank's shard
+        (of the whole batch with `allreduce_loss=True`): a 0-dim CUDA tensor that stays valid for the next
+        `LOSS_RING` steps (call .item() to read it back), or with `async_loss=True` a `PendingLoss` whose `.item()`
+        waits only for a 4-byte copy queued behind this step — read it after launching the next step and the host
+        never stalls the GPU."""
+        with torch.cuda.device(self.device):
+            cur = torch.cuda.current_stream(self.device)
+            args = (x, bbox, vertices, labels, rand_neg_idx, lm_rand_neg_idx)
+            if self._staged is not None and self._staged[0] == self._key(*args):
+                k = self._staged[1]
+                cur.wait_event(self._slot_ready[k])
+                if labels is not None:
+                    self.slots[k]["labels_are_ones"] = False
+            else:
+                k = self._cur
+                if self._pf_stream is not None and self._slot_ready[k] is not None:
+                    cur.wait_event(self._slot_ready[k])  # an unconsumed prefetch into this slot must land first
+                self._fill_slot(k, *args)
+            self._staged = None  # a prefetch that was not consumed is dropped (its key can never match stale memory)
+            clamp_lm = labels is not None  # `_pn` helpers of train_densebox_online (:1899-1907)
+            graph_ok = self.use_graph and self.step_no >= 1  # step 0 runs eagerly (one-time inits, SGD first-step flag)
+            if self.world > 1:
+                self._step_dp(k, clamp_lm, graph_ok)
+            else:
+                self._step_single(k, clamp_lm, graph_ok)
+            j = self.step_no % LOSS_RING
+            out = self._loss_ring[j]
+            out.copy_(self.eng.loss_value())  # an independent value: the engine's scalar is overwritten every step
+            if self.allreduce_loss:
+                torch.distributed.all_reduce(out, group=self.pg)
+            if self._slot_free[k] is None:
+                self._slot_free[k] = torch.cuda.Event()
+            self._slot_free[k].record(cur)
+            self._cur = 1 - k
+            self.step_no += 1
+            if not async_loss:
+                return out
+            self._loss_host[j:j + 1].copy_(out.reshape(1), non_blocking=True)
+            ev = self._loss_events[j]
+            if ev is None:
+                ev = self._loss_events[j] = torch.cuda.Event()
+            ev.record(cur)
+            return PendingLoss(out, self._loss_host[j], ev)
 
     def kernels_per_step(self):
         """Number of this library's kernel launches in one training step (for bench.py's gpu_launches)."""

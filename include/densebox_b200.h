@@ -68,16 +68,32 @@ int dbx_colsum(const void* dy, int N, int H, int W, int C, int cs, int coff, flo
 int dbx_decode_nms(const float* score, long s_img, long s_pix, const float* loc, long l_img, long l_pix, long l_ch,
                    const float* lmloc, long m_img, long m_pix, long m_ch, int N, int H4, int W4, int K, double thresh,
                    float* dets, int* keep, void* stream);
+/* parse_DetLM (DenseBox.py:3220-3300): as above, but the landmarks of every detection are the arg-max positions (x4)
+ * of the four landmark HEAT-maps `lmheat` [.,4,..] (:3283-3292). */
+int dbx_decode_nms_heat(const float* score, long s_img, long s_pix, const float* loc, long l_img, long l_pix, long l_ch,
+                        const float* lmheat, long m_img, long m_pix, long m_ch, int N, int H4, int W4, int K,
+                        double thresh, float* dets, int* keep, void* stream);
 
 /* The fused loss on caller-provided head maps (same semantics as dbx_net_loss below; used by the drop-in
  * densebox_loss() op).  head: fp32 [B,60,60,HC] in the channel map below, rf: fp32 [B,60,60,RC] (variants 1,2).
- * scratch: >= 16 + 4*B bytes of device memory, zeroed once before the first call.  Outputs may be NULL. */
+ * scratch: >= 16 + 4*B bytes of device memory, zeroed once before the first call.  Outputs may be NULL.
+ * info: int[4] = {half, pos, rand_short, 0}. */
 int dbx_loss_fwd_bwd(const float* head, int HC, const float* rf, int RC, const float* bbox, const float* vertices,
                      const float* labels, const long long* rand_idx, int rand_stride, const long long* lm_rand_idx,
                      int variant, float lambda_loc, float lambda_det, float lambda_lm, int global_pos,
                      int global_batch, const int* global_pos_ptr, int clamp_lm, int B, void* scratch, float* loss,
                      int* info, void* d_head_bf16, void* d_rf_bf16, float* d_head_f32, float* d_rf_f32,
                      unsigned char* mask_out, unsigned char* lm_mask_out, void* stream);
+/* The same kernel on the five map groups given one by one with explicit element strides — what densebox_loss() calls
+ * with the NCHW tensors returned by forward(): maps[5] = {score, loc, landmark heat, landmark loc, refine} (NULL where
+ * the variant has none), strides[15] = (image, pixel, channel) per group, grads[5] (optional, same strides) receive
+ * d(loss)/d(map) in fp32.  info: int[4] = {half, pos, rand_short, 0}; rand_short = 1 when the negative quota `half`
+ * exceeds rand_stride, i.e. fewer injected random negatives were available than DenseBox.py:2888-2893 would draw. */
+int dbx_loss_maps(const float* const* maps, const long* strides, float* const* grads, const float* bbox,
+                  const float* vertices, const float* labels, const long long* rand_idx, int rand_stride,
+                  const long long* lm_rand_idx, int variant, float lambda_loc, float lambda_det, float lambda_lm,
+                  int global_pos, int global_batch, const int* global_pos_ptr, int clamp_lm, int B, void* scratch,
+                  float* loss, int* info, unsigned char* mask_out, unsigned char* lm_mask_out, void* stream);
 /* Positive pixels of a label shard (sum of the clipped init_score_map boxes, DenseBox.py:2864) -> *out (device). */
 int dbx_count_positives(const float* bbox, const float* labels, int B, int* out, void* stream);
 /* nn.Dropout(p=0.5) keep-mask x2 as an explicit bf16 tensor — the same Philox4x32-10 bits the conv epilogues draw
@@ -110,6 +126,17 @@ int dbx_net_get_param(void* handle, const char* name, int is_bias, float* dst, l
                       long s_s, void* stream);
 int dbx_net_get_grad(void* handle, const char* name, int is_bias, float* dst, long s_co, long s_ci, long s_r,
                      long s_s, void* stream);
+/* The same for a whole list of tensors in ONE kernel launch (what the drop-in modules use every step): mode 0 = torch
+ * tensors -> engine (fp32 masters + bf16 GEMM copies), 1 = engine masters -> torch tensors, 2 = engine gradients ->
+ * torch tensors.  names[n]; w_ptrs[n] with w_strides[4n] (co, ci, r, s element strides); b_ptrs[n], b_strides[n]. */
+int dbx_net_xfer_params(void* handle, int mode, int n, const char* const* names, void* const* w_ptrs,
+                        const long* w_strides, void* const* b_ptrs, const long* b_strides, void* stream);
+/* forward() return values (DenseBox.py:228, :473, :738) as contiguous NCHW fp32 tensors [N,{1,4,4,8,1},H/4,W/4] copied
+ * out of head_out / rf_out in one launch (NULL = not wanted), and the way back for loss.backward(): the gradients of
+ * those tensors (NULL = zero) packed into the bf16 "d_head" / "d_rf" regions that dbx_net_backward consumes. */
+int dbx_net_get_outputs(void* handle, float* score, float* loc, float* lm, float* lmloc, float* rf, void* stream);
+int dbx_net_set_output_grads(void* handle, const float* g_score, const float* g_loc, const float* g_lm,
+                             const float* g_lmloc, const float* g_rf, void* stream);
 /* Rebuild the flipped/transposed bf16 filters used by the data gradients (after set_param, before backward). */
 int dbx_net_refresh_dgrad(void* handle, void* stream);
 
@@ -142,7 +169,8 @@ int dbx_net_backward(void* handle, void* stream);
  * autograd graph of :2925 is simply cut after conv4_1): stage 0 = refine branch + heads + conv4 block, stage 1 =
  * conv3 .. conv1.  After stage 0 the gradients of bucket 0 are final, so their all-reduce overlaps stage 1.
  * dbx_net_grad_bucket: element range [first, first+count) of "g32" — bucket 0 = filters conv4_1..heads(+refine),
- * 1 = filters conv1_1..conv3_4, 2 = every bias.  dbx_net_join: make `stream` wait for the filter re-layout that
+ * 1 = filters conv1_1..conv3_4, 2 = every bias, 3 = buckets 1 and 2 together (contiguous: one all-reduce for
+ * everything stage 1 completes).  dbx_net_join: make `stream` wait for the filter re-layout that
  * dbx_net_forward forked onto the engine's side stream (needed when forward is captured into its own CUDA graph). */
 int dbx_net_backward_stage(void* handle, int stage, void* stream);
 int dbx_net_grad_bucket(void* handle, int bucket, long long* first, long long* count);

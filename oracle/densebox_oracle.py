@@ -103,50 +103,92 @@ class _StoreBF16(torch.autograd.Function):
         return g.bfloat16().float(), None
 
 
-def _cr(x, P, name, st):
-    return st(F.relu(F.conv2d(x, P[name + ".weight"], P[name + ".bias"], padding=1)))
+def _cr(x, P, name, st, gb=None, frozen=None):
+    z = F.conv2d(x, P[name + ".weight"], P[name + ".bias"], padding=1)
+    if frozen is None:
+        return st(F.relu(z))
+    # frozen decisions: the ReLU mask is the engine's (its stored activation > 0), the value is the engine's, the
+    # gradient path is this graph's; the engine stores d(loss)/dz in bf16 -> round the gradient of z
+    y = gb(z) * (frozen[name] > 0).to(z.dtype)
+    return _subst(y, frozen[name])
 
 
-def _head(fusion, P, head, drop, st):
+def _subst(t, value):
+    """Tensor with the VALUE `value` (what the engine stored) and the gradient path of `t`."""
+    return value + (t - t.detach())
+
+
+def _head(fusion, P, head, drop, st, frozen=None, record=None):
     h = F.conv2d(fusion, P["conv5_1_%s.weight" % head], P["conv5_1_%s.bias" % head])
     if drop is not None:  # train mode: nn.Dropout(p=0.5) == multiply by a {0,2} mask (injected for parity)
         h = h * drop
-    return F.conv2d(st(h), P["conv5_2_%s.weight" % head], P["conv5_2_%s.bias" % head])
+    h = st(h)
+    if frozen is not None:
+        h = _subst(h, frozen["hd_" + head])
+    if record is not None:
+        record["hd_" + head] = h.detach().clone()
+    return F.conv2d(h, P["conv5_2_%s.weight" % head], P["conv5_2_%s.bias" % head])
 
 
-def forward(P, X, variant="densebox", dropout=None, return_intermediates=False, emulate_bf16_storage=False):
+def forward(P, X, variant="densebox", dropout=None, return_intermediates=False, emulate_bf16_storage=False,
+            frozen=None, record=None):
     """Reference forward.  dropout: None (eval) or {head: mask[B,512,h,w] of 0/2} (train).
     emulate_bf16_storage=True additionally rounds every stored activation (and its gradient) to bf16 at the points
-    where the CUDA engine stores bf16 — a test aid, see _StoreBF16; the reference itself is fp32 throughout."""
-    if emulate_bf16_storage:
+    where the CUDA engine stores bf16 — a test aid, see _StoreBF16; the reference itself is fp32 throughout.
+    frozen = {layer: tensor} (a test aid, implies the bf16 emulation): FROZEN-DECISION mode.  Every stored activation
+    takes the value the CUDA engine stored (conv*/up/hd_*/score/loc/lm/lmloc/rp/r1/r2/rup/rf, NCHW fp32 copies of the
+    engine's buffers) and every ReLU mask is the engine's, so all data-dependent decisions of the backward pass (ReLU
+    masks, max-pool arg-maxes — F.max_pool2d on identical values picks identical positions —, mined negatives) are
+    the engine's own and the comparison of parameter gradients is free of the bf16 ReLU/arg-max flip noise: what
+    remains is accumulation order and bf16 rounding of the stored gradients.
+    record = {} collects the detached value of every such stage under the same names (self-test of the frozen mode)."""
+    if emulate_bf16_storage or frozen is not None:
         st = lambda t: _StoreBF16.apply(t, True)      # value and gradient stored as bf16
         gb = lambda t: _StoreBF16.apply(t, False)     # only the gradient is stored as bf16
     else:
         st = gb = lambda t: t
-    x = _cr(X, P, "conv1_1", st); x = _cr(x, P, "conv1_2", st); x = gb(F.max_pool2d(x, 2, 2))
-    x = _cr(x, P, "conv2_1", st); x = _cr(x, P, "conv2_2", st); x = gb(F.max_pool2d(x, 2, 2))
-    x = _cr(x, P, "conv3_1", st); x = _cr(x, P, "conv3_2", st)
-    c34 = _cr(x, P, "conv3_4", st)  # conv3_3 skipped (:193-195)
+    fz = frozen
+
+    def sub(t, name):
+        t = _subst(t, fz[name]) if fz is not None else t
+        if record is not None:
+            record[name] = t.detach().clone()
+        return t
+
+    def cr(x, name):
+        y = _cr(x, P, name, st, gb, fz)
+        if record is not None:
+            record[name] = y.detach().clone()
+        return y
+
+    if record is not None:
+        _rec_heads = record
+    else:
+        _rec_heads = None
+    x = cr(X, "conv1_1"); x = cr(x, "conv1_2"); x = gb(F.max_pool2d(x, 2, 2))
+    x = cr(x, "conv2_1"); x = cr(x, "conv2_2"); x = gb(F.max_pool2d(x, 2, 2))
+    x = cr(x, "conv3_1"); x = cr(x, "conv3_2")
+    c34 = cr(x, "conv3_4")  # conv3_3 skipped (:193-195)
     x = gb(F.max_pool2d(c34, 2, 2))
-    x = _cr(x, P, "conv4_1", st); x = _cr(x, P, "conv4_2", st); x = _cr(x, P, "conv4_3", st)
-    c44 = _cr(x, P, "conv4_4", st)
-    up = st(F.interpolate(c44, size=(c34.shape[2], c34.shape[3]), mode="bilinear", align_corners=True))
+    x = cr(x, "conv4_1"); x = cr(x, "conv4_2"); x = cr(x, "conv4_3")
+    c44 = cr(x, "conv4_4")
+    up = sub(st(F.interpolate(c44, size=(c34.shape[2], c34.shape[3]), mode="bilinear", align_corners=True)), "up")
     fusion = gb(torch.cat((up, c34), dim=1))  # upsampled conv4_4 first (:219)
     d = dropout or {}
-    score = gb(_head(fusion, P, "det", d.get("det"), st))
-    loc = gb(_head(fusion, P, "loc", d.get("loc"), st))
+    score = sub(gb(_head(fusion, P, "det", d.get("det"), st, fz, _rec_heads)), "score")
+    loc = sub(gb(_head(fusion, P, "loc", d.get("loc"), st, fz, _rec_heads)), "loc")
     inter = {"conv3_4": c34, "conv4_4": c44, "fusion": fusion}
     if variant == "densebox":
         out = (score, loc)
     else:
-        lm = gb(_head(fusion, P, "landmark", d.get("landmark"), st))
-        lmloc = gb(_head(fusion, P, "lmloc", d.get("lmloc"), st)) if variant == "lmloc" else None
+        lm = sub(gb(_head(fusion, P, "landmark", d.get("landmark"), st, fz, _rec_heads)), "lm")
+        lmloc = sub(gb(_head(fusion, P, "lmloc", d.get("lmloc"), st, fz, _rec_heads)), "lmloc") if variant == "lmloc" else None
         x = torch.cat((lm, score), dim=1)
-        x = st(F.max_pool2d(x, 2, 2))
-        x = st(F.conv2d(x, P["conv6_1_det.weight"], P["conv6_1_det.bias"]))
-        x = st(F.conv2d(x, P["conv6_2_det.weight"], P["conv6_2_det.bias"]))
-        x = st(F.interpolate(x, size=(score.shape[2], score.shape[3]), mode="bilinear", align_corners=True))
-        rf = gb(F.conv2d(x, P["conv6_3_det.weight"], P["conv6_3_det.bias"]))
+        x = sub(st(F.max_pool2d(x, 2, 2)), "rp")
+        x = sub(st(F.conv2d(x, P["conv6_1_det.weight"], P["conv6_1_det.bias"])), "r1")
+        x = sub(st(F.conv2d(x, P["conv6_2_det.weight"], P["conv6_2_det.bias"])), "r2")
+        x = sub(st(F.interpolate(x, size=(score.shape[2], score.shape[3]), mode="bilinear", align_corners=True)), "rup")
+        rf = sub(gb(F.conv2d(x, P["conv6_3_det.weight"], P["conv6_3_det.bias"])), "rf")
         out = (score, loc, lm, rf) if variant == "lm" else (score, rf, loc, lm, lmloc)  # return orders :473, :738
     return (out, inter) if return_intermediates else out
 
@@ -338,10 +380,17 @@ def loss(outs, variant, bbox, rand_idx, vertices=None, lm_rand_idx=None, labels=
 
 
 # ------------------------------------------------------------------------------------------------ decode + NMS
-def decode(score_map, loc_map, lmloc_map=None, K=10):
-    """parse_out_MN / parse_DetLMLOC (:3114-3217): top-K of the raw score map, boxes (and landmarks) decoded x4.
-    Maps are torch [1,C,h,w]; returns float64 numpy [K, 5 or 13]."""
+def decode(score_map, loc_map, lmloc_map=None, K=10, lmheat_map=None):
+    """parse_out_MN / parse_DetLMLOC (:3114-3217): top-K of the raw score map, boxes (and landmarks) decoded x4;
+    lmheat_map given: parse_DetLM (:3220-3300) — the landmarks of every row are the arg-max positions of the four
+    landmark heat-maps x4.  Maps are torch [1,C,h,w]; returns float64 numpy [K, 5 or 13]."""
     h, w = score_map.shape[2], score_map.shape[3]
+    heat_lms = []
+    if lmheat_map is not None:
+        for k in range(4):
+            _, li = torch.topk(lmheat_map[0, k].reshape(-1), 1)  # :3285
+            li = int(li)
+            heat_lms += [float(li % w) * 4.0, float(li // w) * 4.0]
     s = score_map.reshape(-1)
     vals, idx = torch.topk(s, K)
     dets = []
@@ -354,6 +403,7 @@ def decode(score_map, loc_map, lmloc_map=None, K=10):
         if lmloc_map is not None:
             for k in range(4):
                 row += [sub(xi, lmloc_map, 2 * k) * 4.0, sub(yi, lmloc_map, 2 * k + 1) * 4.0]
+        row += heat_lms
         dets.append(row)
     return np.asarray(dets, dtype=np.float64)
 

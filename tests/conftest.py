@@ -4,6 +4,9 @@ import sys
 import pytest
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+# the library honours its A/B environment switches (DBX_FUSE_BIAS, ...) only when this is set before first use;
+# test_gpu_fused_bias.py flips three of them to cross-check independent implementations of the same result
+os.environ.setdefault("DBX_ENABLE_AB", "1")
 
 
 def pytest_configure(config):

@@ -9,7 +9,9 @@ The reference ships no tests or golden vectors, so the oracle is
   * loss_*.npz     — the loop bodies train_online / train_LM_online / train_LMLOC_online / train_densebox_online driven
                      with the reference's own helper functions on random head maps (np.random.choice draws injected)
   * forward_*.npz  — DenseBox / DenseBoxLM / DenseBoxLMLOC modules of the reference on the seeded KAT input
-  * decode_nms.npz — parse_out_MN / parse_DetLMLOC / NMS
+  * decode_nms.npz — parse_out_MN / parse_DetLMLOC / parse_DetLM / NMS
+  * state_dict.npz — key -> shape of the three modules' state_dict() and the outcome of a strict load_state_dict round
+                     trip between the reference modules and the drop-in modules (both directions)
 Loading shims: matplotlib stub, CUDA hidden during import, float64 labels for the loc-map
 generators under NumPy >= 2.  Nothing of the reference is copied; only its outputs are stored.
 """
@@ -205,6 +207,7 @@ def gen_decode(REF):
     lml = torch.randn(1, 8, M // 4, N // 4, generator=g) * 5
     d1 = REF.parse_out_MN(score, loc, M, N, K=10)
     d2 = REF.parse_DetLMLOC(score, loc, lmh, lml, M, N, K=10)
+    d3 = REF.parse_DetLM(score, loc, lmh, M, N, K=10)
     rs = np.random.RandomState(5)
     boxes = []
     for _ in range(40):
@@ -214,13 +217,42 @@ def gen_decode(REF):
     keep = [REF.NMS(boxes, t) for t in (0.2, 0.4, 0.6)]
     kat = REF.NMS(np.array([[0, 0, 10, 10, .9], [1, 1, 11, 11, .8], [50, 50, 60, 60, .7]]), 0.4)
     np.savez_compressed(os.path.join(HERE, "decode_nms.npz"), score=score.numpy(), loc=loc.numpy(), lmh=lmh.numpy(),
-                        lml=lml.numpy(), dets_mn=np.asarray(d1), dets_lmloc=np.asarray(d2), boxes=boxes,
+                        lml=lml.numpy(), dets_mn=np.asarray(d1), dets_lmloc=np.asarray(d2), dets_lm=np.asarray(d3), boxes=boxes,
                         keep02=np.array(keep[0]), keep04=np.array(keep[1]), keep06=np.array(keep[2]),
                         kat_keep=np.array(kat))
 
 
+def gen_state_dict(REF):
+    """Checkpoint compatibility (DenseBox.py:1938-1945, :1989-1994): the drop-in modules must load a reference
+    checkpoint and save one the reference loads — strict, both ways — and carry the same values afterwards."""
+    import torchvision
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    import densebox_b200
+    d = {}
+    for variant, cls in (("densebox", "DenseBox"), ("lm", "DenseBoxLM"), ("lmloc", "DenseBoxLMLOC")):
+        torch.manual_seed(0)
+        vgg = torchvision.models.vgg19(weights=None)
+        torch.manual_seed(1)
+        ref = getattr(REF, cls)(vgg)
+        torch.manual_seed(2)
+        ours = getattr(densebox_b200, cls)(vgg)
+        sd_ref = ref.state_dict()
+        r1 = ours.load_state_dict(sd_ref, strict=True)          # reference checkpoint -> drop-in module
+        same1 = all(torch.equal(v, sd_ref[k]) for k, v in ours.state_dict().items())
+        torch.manual_seed(3)
+        ours2 = getattr(densebox_b200, cls)(vgg)
+        r2 = ref.load_state_dict(ours2.state_dict(), strict=True)  # drop-in checkpoint -> reference module
+        same2 = all(torch.equal(v, ours2.state_dict()[k]) for k, v in ref.state_dict().items())
+        d[variant + "_keys"] = np.array(list(sd_ref.keys()))
+        d[variant + "_shapes"] = np.array([",".join(map(str, v.shape)) for v in sd_ref.values()])
+        d[variant + "_roundtrip_ok"] = np.array([not r1.missing_keys and not r1.unexpected_keys and same1,
+                                                 not r2.missing_keys and not r2.unexpected_keys and same2])
+    np.savez_compressed(os.path.join(HERE, "state_dict.npz"), **d)
+
+
 if __name__ == "__main__":
     REF = load_reference()
+    gen_state_dict(REF)
     gen_geometry(REF)
     gen_loss(REF)
     gen_decode(REF)

@@ -96,6 +96,7 @@ def test_decode_and_nms_bit_exact():
     t = lambda k: torch.from_numpy(d[k])
     assert np.array_equal(O.decode(t("score"), t("loc"), None, K=10), d["dets_mn"])
     assert np.array_equal(O.decode(t("score"), t("loc"), t("lml"), K=10), d["dets_lmloc"])
+    assert np.array_equal(O.decode(t("score"), t("loc"), None, K=10, lmheat_map=t("lmh")), d["dets_lm"])
     for key, th in (("keep02", 0.2), ("keep04", 0.4), ("keep06", 0.6)):
         assert O.nms(d["boxes"], th) == d[key].tolist()
     kat = np.array([[0, 0, 10, 10, .9], [1, 1, 11, 11, .8], [50, 50, 60, 60, .7]])
@@ -112,3 +113,34 @@ def test_state_dict_keys_match_reference():
         keys = sorted(net.state_dict().keys())
         assert len(keys) == n == int(d["n_keys"])
         assert keys == [str(k) for k in d["keys"]]
+
+
+def test_state_dict_shapes_and_checkpoint_round_trip():
+    """Checkpoint compatibility (DenseBox.py:1938-1945, :1989-1994): same keys IN THE SAME ORDER with the same shapes
+    as the reference's state_dict(); make_golden.py loaded a reference checkpoint into the drop-in modules and a
+    drop-in checkpoint into the reference modules (strict, values compared) and stored the outcome.  When the
+    reference is present (the build container) the round trip is repeated live."""
+    import densebox_b200
+    d = np.load(os.path.join(G, "state_dict.npz"))
+    vgg = O.seeded_vgg19(0)
+    for variant, cls in (("densebox", "DenseBox"), ("lm", "DenseBoxLM"), ("lmloc", "DenseBoxLMLOC")):
+        assert d[variant + "_roundtrip_ok"].all()
+        sd = getattr(densebox_b200, cls)(vgg).state_dict()
+        assert list(sd.keys()) == [str(k) for k in d[variant + "_keys"]]
+        assert [",".join(map(str, v.shape)) for v in sd.values()] == [str(x) for x in d[variant + "_shapes"]]
+    if not os.path.isdir("/root/reference"):
+        return
+    sys.path.insert(0, G)
+    import make_golden
+    REF = make_golden.load_reference()
+    torch.manual_seed(5)
+    ref = REF.DenseBoxLM(vgg)
+    torch.manual_seed(6)
+    ours = densebox_b200.DenseBoxLM(vgg)
+    ours.load_state_dict(ref.state_dict(), strict=True)
+    x = torch.randn(1, 3, 240, 240, generator=torch.Generator().manual_seed(9))
+    with torch.no_grad():
+        want = ref.eval()(x)
+        got = O.forward(O.params_from_state_dict(ours.state_dict(), "lm"), x, "lm")
+    for a, b in zip(got, want):
+        np.testing.assert_allclose(a.numpy(), b.numpy(), rtol=1e-4, atol=1e-4)

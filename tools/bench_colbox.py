@@ -1,5 +1,6 @@
 """A/B of the column-box fprop mode (DBX_COLBOX_FPROP) on the narrow 3x3 layers; checks it against the generic mode."""
 import os
+os.environ["DBX_ENABLE_AB"] = "1"  # the library honours its A/B switches only when this is set
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

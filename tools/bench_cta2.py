@@ -1,5 +1,6 @@
 """A/B of CTA pairs (tcgen05.mma.cta_group::2) on the narrow-N fprop/dgrad shapes (B=32, 240x240 patches)."""
 import os
+os.environ["DBX_ENABLE_AB"] = "1"  # the library honours its A/B switches only when this is set
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

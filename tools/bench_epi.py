@@ -1,6 +1,7 @@
 """A/B of the TMA-staged epilogue vs the direct (registers -> global, no block barrier) epilogue on the layers whose
 pace is set by the epilogue."""
 import os
+os.environ["DBX_ENABLE_AB"] = "1"  # the library honours its A/B switches only when this is set
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

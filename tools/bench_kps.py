@@ -1,5 +1,6 @@
 """A/B of K blocks per pipeline stage (DBX_KPS) on the fprop/dgrad shapes of the bench (B=32, 240x240 patches)."""
 import os
+os.environ["DBX_ENABLE_AB"] = "1"  # the library honours its A/B switches only when this is set
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

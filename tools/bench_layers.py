@@ -2,6 +2,7 @@
 Prints ms and TFLOP/s for fprop and wgrad of every conv on the hot path. Inputs are larger than L2 for the big
 layers; CUDA events on the current stream; 3 warm-up + 10 timed launches each."""
 import os
+os.environ["DBX_ENABLE_AB"] = "1"  # the library honours its A/B switches only when this is set
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

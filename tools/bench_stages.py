@@ -1,5 +1,6 @@
 """Throughput of one fprop shape as a function of pipeline depth (DBX_STAGES) — latency-bound or not?"""
 import os
+os.environ["DBX_ENABLE_AB"] = "1"  # the library honours its A/B switches only when this is set
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

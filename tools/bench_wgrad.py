@@ -1,5 +1,6 @@
 """wgrad variants on the bench shapes: default dispatch, column-box forced on/off, block_n 192/256; cross-checked."""
 import os
+os.environ["DBX_ENABLE_AB"] = "1"  # the library honours its A/B switches only when this is set
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
