@@ -53,6 +53,8 @@ def headline_config(world, graph=True):
             "variant": "densebox", "per_gpu_batch": 32, "global_batch": 32 * world, "parallelism": "dp%d" % world,
             "step": "fwd + fused loss + bwd + grad allreduce(sum) + SGD",
             "cache": "inputs larger than L2: one step streams ~3.6 GB of activations per GPU >> 126 MB L2 (no flush needed)",
+            "timing": "CUDA events around K steps between two barriers; every timed region starts after 1 s of idle (same "
+                      "power state for value and e2e); steady state under the power cap: record `sustained`",
             "cuda_graph": graph, "weights": "seeded vgg19(weights=None) + xavier heads",
             "optimizer": "SGD lr=1e-9 m=0.9 wd=5e-8 (DenseBox.py:2821-2824)"}
 
@@ -216,7 +218,7 @@ def make_net(variant, dev):
     return getattr(densebox_b200, CLS[variant])(vgg).to(dev)
 
 
-def timed_steps(c, tr, batches, steps, host, sampler=None):
+def timed_steps(c, tr, batches, steps, host, sampler=None, gap=1.0):
     """`steps` training steps, CUDA events on the launching stream between two barriers; returns ms per step (this
     rank) and the last loss.  host=True: pinned host batches through prefetch() + asynchronous loss read-back."""
     import torch
@@ -226,6 +228,13 @@ def timed_steps(c, tr, batches, steps, host, sampler=None):
         return dict(vertices=b.get("vertices"), rand_neg_idx=b["rand"], lm_rand_neg_idx=b.get("lm_rand"))
 
     c.barrier()
+    if gap:
+        # Equal power state for every timed region: a region that starts right behind another one inherits its
+        # clocks (tools/e2e_probe.py: the SECOND of two back-to-back 20-step regions runs at ~1 650 MHz instead of
+        # 1 965 and reads 6-8 % slower, whichever of value / e2e it is; after 1 s of idle they agree within 0.4 %).
+        # The power-capped steady state is reported separately (`sustained`).
+        time.sleep(gap)
+        c.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.time()
     e0.record()
@@ -397,7 +406,7 @@ def run_training(c, variant, B, steps, warmup, pg, graph=True, parity=False, pro
 def run_sustained(c, steps):
     """>= 300 steps of the headline workload on the trainer of the main run: the power-capped steady state."""
     tr, net, batches, dev_batches = c.keep
-    ms, loss, clocks = timed_steps(c, tr, dev_batches, steps, host=False, sampler=c.sampler)
+    ms, loss, clocks = timed_steps(c, tr, dev_batches, steps, host=False, sampler=c.sampler, gap=0.0)
     B = tr.B
     tf = GFLOP_TRAIN["densebox"] * B / ms
     return {"steps": steps, "value": round(B / (ms * 1e-3), 1), "unit": "patches/s", "ms_per_step": round(ms, 4),
@@ -424,6 +433,7 @@ def run_inference(c, variant="lmloc", N=16, HW=1024, steps=5, warmup=2):
     out = {}
     for name, src in (("value", x_dev), ("e2e", x_host)):
         torch.cuda.synchronize()
+        time.sleep(1.0)  # same power state for both regions (see timed_steps)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
@@ -464,6 +474,7 @@ def run_dropin(c, B=32, steps=10, warmup=3):
     for i in range(warmup):
         step(batches[i % 2])
     torch.cuda.synchronize()
+    time.sleep(1.0)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(steps):
