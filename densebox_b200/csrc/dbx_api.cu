@@ -86,6 +86,17 @@ int dbx_loss_maps(const float* const* maps, const long* strides, float* const* g
   return loss_fwd_bwd(p, (cudaStream_t)stream);
 }
 
+int dbx_count_exchange(const float* bbox, const float* labels, int B, void* const* peer_slots, int world, int rank,
+                       void* local_slots, void* stream) {
+  if (!peer_slots || world < 1 || world > 16) return DBX_ERR_ARG;
+  PeerSlots ps{};
+  ps.world = world; ps.rank = rank;
+  for (int r = 0; r < world; ++r) ps.p[r] = (unsigned long long*)peer_slots[r];
+  return count_exchange(bbox, labels, B, ps, (unsigned long long*)local_slots, (cudaStream_t)stream);
+}
+
+int dbx_set_tensor_sm_limit(int n) { return set_tensor_sm_limit(n); }
+
 int dbx_count_positives(const float* bbox, const float* labels, int B, int* out, void* stream) {
   return count_positives(bbox, labels, B, out, (cudaStream_t)stream);
 }

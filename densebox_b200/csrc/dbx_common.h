@@ -41,6 +41,8 @@ int encode_act_map(CUtensorMap* m, const Act& a, const Tile& t);                
 int encode_mat_map(CUtensorMap* m, const void* ptr, int rows, int cols, int box_rows); // 2D (cols, rows), box (64, box_rows)
 
 int num_sms();          // of the CURRENT device (cached per device)
+int tensor_sms();       // SMs the persistent tcgen05 kernels may use: num_sms() capped by set_tensor_sm_limit(), even
+int set_tensor_sm_limit(int n);  // 0 = no limit; returns the previous value
 bool pdl_enabled();
 // A/B measurement switches (DBX_* environment variables read by the launchers) are honoured only when the process
 // sets DBX_ENABLE_AB=1 before the library is first used; otherwise this returns nullptr for every name, so the kernel
@@ -164,6 +166,8 @@ struct LossParams {
   float lambda_loc, lambda_det, lambda_lm;
   int global_pos, global_batch;   // data-parallel: batch-global positive count / batch size; <0 = use this launch
   const int* global_pos_ptr;      // optional device int: overrides global_pos (filled by count_positives + allreduce)
+  const unsigned long long* count_slots; int count_world;  // optional: step-tagged per-rank counts written by the peers
+                                  // (count_exchange): [2][world] slots + the local step counter at [2 * world]
   int clamp_lm;                   // init_lm_heatmap_pn clamping (:1899-1907)
   int B;
   float* loss_partial;            // [B]
@@ -180,6 +184,12 @@ struct LossParams {
 };
 int loss_fwd_bwd(const LossParams& p, cudaStream_t st);
 int count_positives(const float* bbox, const float* labels, int B, int* out, cudaStream_t st);
+// Data parallel without a collective on the critical path: the positives of this rank's shard are written, tagged with
+// the step number, straight into the slot buffer of EVERY rank (peer stores over NVLink; peers[r] = rank r's buffer,
+// local = this rank's); the loss kernel of each rank sums the slots of the step (LossParams::count_slots).
+struct PeerSlots { unsigned long long* p[16]; int world, rank; };
+int count_exchange(const float* bbox, const float* labels, int B, const PeerSlots& peers, unsigned long long* local,
+                   cudaStream_t st);
 
 
 // ---- detection post-processing (dbx_postproc.cu); maps are fp32 with explicit image/pixel/channel element strides

@@ -290,7 +290,7 @@ int conv3x3_halo(const Act& x, const void* wk, const Act& out, const ConvEpilogu
   static SmemAttrOnce attr_once;
   { const int arc = set_max_smem_once((const void*)conv3x3_halo_kernel, kHaloSmem + 1024, &attr_once); if (arc) return arc; }
   const int total = p.m_tiles * p.n_tiles;
-  const int grid = total < num_sms() ? total : num_sms();
+  const int grid = total < tensor_sms() ? total : tensor_sms();
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kHaloThreads); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
   cudaLaunchAttribute attr[1];

@@ -288,39 +288,115 @@ __device__ __forceinline__ Lin lin_coord(int d, float scale, int in_size) {
   return r;
 }
 
-// One block per output row (n, oy): the row's vertical coordinates are hoisted, every thread walks (pixel, 8-channel
-// vector) pairs 256 apart so a warp stores 512 contiguous bytes per instruction, four vectors in flight per thread.
-__global__ void __launch_bounds__(256) upsample_fwd_kernel(Act in, Act out, float sh, float sw) {
+// Forward.  A thread owns one 8-channel vector of a run of `len` horizontally adjacent output pixels of one output row
+// and walks the run left to right holding the two VERTICALLY blended input columns it sits between in registers
+// (bilinear interpolation is separable); a column is loaded once per run — about one 2 x 16-byte load pair per two
+// outputs instead of four loads per output.  The round-1 kernel (4 loads + 4 unpacks + 6 FMA groups per output, an
+// integer division per item, 1.6 waves of one-row blocks) issued at 72 % of the SM's instruction rate and reached
+// 42 % of the HBM roofline; the instruction count per output is less than half here and the run length is chosen so
+// that the grid fills whole waves.
+__global__ void __launch_bounds__(256) upsample_fwd_kernel(Act in, Act out, float sh, float sw, int len, int nseg,
+                                                           size_t total) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
   const int cc = out.C / 8;
-  const int oy = (int)(blockIdx.x % out.H), n = (int)(blockIdx.x / out.H);
+  const int cvec = (int)(idx % cc);
+  size_t t = idx / cc;
+  const int seg = (int)(t % nseg); t /= nseg;
+  const int oy = (int)(t % out.H), n = (int)(t / out.H);
+  const int c = cvec * 8;
   const Lin ly = lin_coord(oy, sh, in.H);
-  const bf16* r0 = at(in, n, ly.i0, 0, 0);
-  const bf16* r1 = at(in, n, ly.i1, 0, 0);
-  bf16* orow = at(out, n, oy, 0, 0);
-  const int total = out.W * cc;
-  for (int v = threadIdx.x; v < total; v += 256) {
-    const int ox = v / cc, c = (v - ox * cc) * 8;
-    const Lin lx = lin_coord(ox, sw, in.W);
-    float a[8], b[8], c0[8], d[8], o[8];
-    unpack8(ldg16(r0 + (size_t)lx.i0 * in.cs + c), a);
-    unpack8(ldg16(r0 + (size_t)lx.i1 * in.cs + c), b);
-    unpack8(ldg16(r1 + (size_t)lx.i0 * in.cs + c), c0);
-    unpack8(ldg16(r1 + (size_t)lx.i1 * in.cs + c), d);
+  const bf16* r0 = at(in, n, ly.i0, 0, c);
+  const bf16* r1 = at(in, n, ly.i1, 0, c);
+  bf16* orow = at(out, n, oy, 0, c);
+  const int x0 = seg * len;
+  int x1 = x0 + len; if (x1 > out.W) x1 = out.W;
+  float va[8], vb[8];
+  auto loadblend = [&](int ix, float* v) {
+    float a[8], b[8];
+    unpack8(ldg16(r0 + (size_t)ix * in.cs), a);
+    unpack8(ldg16(r1 + (size_t)ix * in.cs), b);
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
-      o[j] = ly.l0 * (lx.l0 * a[j] + lx.l1 * b[j]) + ly.l1 * (lx.l0 * c0[j] + lx.l1 * d[j]);
-    *reinterpret_cast<uint4*>(orow + (size_t)ox * out.cs + c) = pack8(o);
+    for (int j = 0; j < 8; ++j) v[j] = ly.l0 * a[j] + ly.l1 * b[j];
+  };
+  Lin lx = lin_coord(x0, sw, in.W);
+  int ci0 = lx.i0, ci1 = lx.i1;
+  loadblend(ci0, va);
+  if (ci1 != ci0) loadblend(ci1, vb);
+  else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) vb[j] = va[j];
   }
+  for (int ox = x0; ox < x1; ++ox) {
+    lx = lin_coord(ox, sw, in.W);
+    if (lx.i0 != ci0) {
+      if (lx.i0 == ci1) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) va[j] = vb[j];
+      } else {
+        loadblend(lx.i0, va);
+      }
+      ci0 = lx.i0;
+    }
+    if (lx.i1 != ci1) {
+      if (lx.i1 == ci0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) vb[j] = va[j];
+      } else {
+        loadblend(lx.i1, vb);
+      }
+      ci1 = lx.i1;
+    }
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = lx.l0 * va[j] + lx.l1 * vb[j];
+    *reinterpret_cast<uint4*>(orow + (size_t)ox * out.cs) = pack8(o);
+  }
+}
+
+// Run length for the walking kernels: as long as possible (fewer redundant loads at the run boundaries) while the grid
+// still fills (nearly) whole waves of `slots` resident blocks.
+static int choose_run(int W, size_t items_per_run, int block, int slots, int min_len) {
+  int best = W, best_nseg = 1;
+  double best_cost = 1e30;
+  for (int nseg = 1; nseg <= W; ++nseg) {
+    const int len = (W + nseg - 1) / nseg;
+    if (len < min_len && nseg > 1) break;
+    const int ns = (W + len - 1) / len;
+    const double blocks = (double)((items_per_run * ns + block - 1) / block);
+    const double waves = blocks / slots;
+    // latency hiding needs a few resident blocks per slot over the kernel's life: below ~2.5 waves the kernel is
+    // latency-bound (measured: one 60-pixel run per thread = 0.65 waves ran at 38 % warp occupancy, 40 us)
+    const double quant = (waves < 2.5 ? 2.5 / (waves > 0.05 ? waves : 0.05) : 1.0) * ceil(waves) / waves;
+    const double cost = quant * (1.0 + 1.5 / len);
+    if (cost < best_cost) { best_cost = cost; best = len; best_nseg = ns; }
+  }
+  (void)best_nseg;
+  return best;
 }
 
 int upsample_bilinear_fwd(const Act& in, const Act& out, cudaStream_t st) {
   if (in.C != out.C || in.N != out.N || in.C % 8) return DBX_ERR_ARG;
   const float sh = out.H > 1 ? (float)(in.H - 1) / (float)(out.H - 1) : 0.f;
   const float sw = out.W > 1 ? (float)(in.W - 1) / (float)(out.W - 1) : 0.f;
-  upsample_fwd_kernel<<<out.N * out.H, 256, 0, st>>>(in, out, sh, sw);
+  const int cc = out.C / 8;
+  static int occ[kMaxDevices] = {0};
+  int dev = 0; cudaGetDevice(&dev); if (dev < 0 || dev >= kMaxDevices) dev = 0;
+  if (!occ[dev]) {
+    int b = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, upsample_fwd_kernel, 256, 0);
+    occ[dev] = b > 0 ? b : 4;
+  }
+  const int len = choose_run(out.W, (size_t)out.N * out.H * cc, 256, occ[dev] * num_sms(), 4);
+  const int nseg = (out.W + len - 1) / len;
+  const size_t total = (size_t)out.N * out.H * nseg * cc;
+  upsample_fwd_kernel<<<grid_for(total, 256), 256, 0, st>>>(in, out, sh, sw, len, nseg, total);
   return (int)cudaGetLastError();
 }
 
+// Backward.  (A register-walking adjoint of the forward kernel — two input rows per thread, vertical taps first — was
+// measured in round 2 at 0.128 ms against 0.089 ms for this gather: 120 registers, 16 warps per SM and one exposed
+// memory round trip per output column made it latency-bound at 25 % issue utilisation; the gather below stays.)
 // din[n,iy,ix,:] = relu'(y) * sum over output pixels of their bilinear weight on (iy,ix) — a gather, so no atomics.
 // One block per input row (n, iy).  The (output index, weight) lists of the row and of every input column are built
 // once per block in shared memory (a few entries each: an input pixel is touched by <= ceil(2/scale)+1 outputs per
@@ -477,9 +553,12 @@ int colsum(const Act& dy, float* db, cudaStream_t st) {
 // ------------------------------------------------------------------------------------------------ heads: dgrad of conv5_2
 // d_hd[pix][i] = drop(pix, i) * sum_c d_head[pix][c] * W2[c][i]  (DenseBox.py:149-178 backward: conv5_2_* then
 // Dropout).  W2 is block-diagonal (head h owns rows ch_start[h] .. ch_start[h+1]-1 and columns 512h .. 512h+511), so a
-// column needs at most 8 products: this is a 236 MB store, not a GEMM — as a K = 64 tensor-core launch it was bound
-// by its epilogue (0.115 ms); here a thread owns 16 channels (one 32-byte sector per store pair), streams pixels, and
-// also folds the bias gradient of conv5_1 (column sums of what it stores) so d_hd is not read back for it.
+// column needs at most 8 products: this is a 236 MB store, not a GEMM.  As a K = 64 tensor-core launch it was paced by
+// its epilogue (0.109 ms = 2.2 TB/s, plus 0.052 ms for the stand-alone column sums of d_hd that give the bias gradient
+// of conv5_1).  Here a thread owns 16 channels (one 32-byte sector per store pair) of TWO pixels per iteration, the
+// head's weights sit in shared memory as conflict-free float4 rows, ONE Philox call serves the 128 channels of eight
+// neighbouring threads (warp shuffles; the round-1 version drew it per thread and was instruction-bound at 0.18 ms),
+// dropout acts on packed bf16x2 words, and the column sums of what is stored come out of the same pass.
 struct Heads2DgradParams {
   const bf16* d_head;      // [pixels][64] bf16 (channels >= HC are zero)
   const bf16* wd;          // [K][64] bf16: wd[i][c] = W2[c][i]
@@ -492,64 +571,115 @@ struct Heads2DgradParams {
   size_t pixels;
 };
 
+// 16 keep-bits -> 8 packed bf16x2 words scaled by {0, 2} (x2 and x0 are exact in bf16)
+__device__ __forceinline__ void dropout8(uint32_t* pk, uint32_t bits) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    // bit 2i -> 0x4000 (bf16 2.0, low half), bit 2i+1 -> 0x40000000 (high half): two shifts and one select-by-mask
+    const uint32_t a = (14 - 2 * i) >= 0 ? (bits << ((14 - 2 * i) & 31)) : (bits >> ((2 * i - 14) & 31));
+    const uint32_t b = bits << ((29 - 2 * i) & 31);
+    const uint32_t m = ((a & 0x00004000u) | (b & 0x40000000u));
+    __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&pk[i]);
+    const __nv_bfloat162 mm = *reinterpret_cast<const __nv_bfloat162*>(&m);
+    v = __hmul2(v, mm);
+    pk[i] = *reinterpret_cast<uint32_t*>(&v);
+  }
+}
+
 __global__ void __launch_bounds__(256) heads2_dgrad_kernel(const Heads2DgradParams p) {
-  extern __shared__ float ws[];  // [8][K]: ws[c][i] = W2[ch_start[head(i)] + c][i] (0 beyond the head's rows)
+  extern __shared__ float4 ws4[];  // [(c * 4 + q) * tpp + t16]: channels 16 t16 + 4 q .. + 3 of product row c
   __shared__ float red[256 * 8];
   const int K = p.K;
+  const int tpp = K / 16;                       // threads per pixel
+  const int ppb = (int)blockDim.x / tpp;        // pixel slots per block
+  float* wsf = reinterpret_cast<float*>(ws4);
   for (int e = threadIdx.x; e < 8 * K; e += blockDim.x) {
     const int c = e / K, i = e - c * K, h = i >> 9;
     int c0 = 0, nc = 0;
 #pragma unroll
     for (int k = 0; k < 4; ++k) if (h == k) { c0 = p.ch_start[k]; nc = p.ch_start[k + 1] - c0; }
-    ws[e] = c < nc ? __bfloat162float(p.wd[(size_t)i * 64 + c0 + c]) : 0.f;
+    const float v = c < nc ? __bfloat162float(p.wd[(size_t)i * 64 + c0 + c]) : 0.f;
+    wsf[(((c * 4 + ((i >> 2) & 3)) * tpp + (i >> 4)) << 2) + (i & 3)] = v;
   }
   __syncthreads();
-  const int tpp = K / 16;                       // threads per pixel
-  const int ppb = (int)blockDim.x / tpp;        // pixel slots per block
-  const int slot = (int)threadIdx.x / tpp, i0 = ((int)threadIdx.x - slot * tpp) * 16;
+  const int slot = (int)threadIdx.x / tpp, t16 = (int)threadIdx.x - slot * tpp, i0 = t16 * 16;
   const int h = i0 >> 9;
   int c0 = 0, nc = 0;
 #pragma unroll
   for (int k = 0; k < 4; ++k) if (h == k) { c0 = p.ch_start[k]; nc = p.ch_start[k + 1] - c0; }
   unsigned long long seed = 0, off = 0;
   if (p.drop_mode == 3) { seed = p.rng[0]; off = p.rng[1]; }
+  const int lane = threadIdx.x & 31;
+  // Philox: one call yields the keep-bits of 128 channels = the 8 lanes of a group.  A warp handles its 512 channels
+  // of EIGHT pixels per batch: lane l draws for pixel (l & 7) and channel group (l >> 3), i.e. every lane does one
+  // useful call per batch (a leader-only call would still cost the whole warp its ~110 instructions), and the lanes of
+  // a group fetch the draw of pixel j from lane (group * 8 + j) with shuffles.
+  const int grp0 = lane & ~7;
+  const uint32_t wsel = (uint32_t)(lane & 7) >> 1, wshift = (uint32_t)(lane & 1) * 16u;
+  const unsigned long long wch = (unsigned long long)((t16 - lane) * 16 + 128 * (lane >> 3));  // first channel of the lane's draw
   float bsum[16];
 #pragma unroll
   for (int j = 0; j < 16; ++j) bsum[j] = 0.f;
   if (slot < ppb)
-  for (size_t pix = (size_t)blockIdx.x * ppb + slot; pix < p.pixels; pix += (size_t)gridDim.x * ppb) {
-    float acc[16];
-#pragma unroll
-    for (int j = 0; j < 16; ++j) acc[j] = 0.f;
-    const bf16* g = p.d_head + pix * 64 + c0;
-    for (int c = 0; c < nc; ++c) {
-      const float gv = __bfloat162float(g[c]);
-      const float4* w4 = reinterpret_cast<const float4*>(ws + (size_t)c * K + i0);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float4 w = w4[q];
-        acc[4 * q] += gv * w.x; acc[4 * q + 1] += gv * w.y; acc[4 * q + 2] += gv * w.z; acc[4 * q + 3] += gv * w.w;
-      }
-    }
+  for (size_t base = ((size_t)blockIdx.x * ppb + slot) * 8; base < p.pixels; base += (size_t)gridDim.x * ppb * 8) {
+    uint4 r = make_uint4(0u, 0u, 0u, 0u);
     if (p.drop_mode == 3) {
-      const uint32_t bits = dropout_bits16(pix * (unsigned long long)K + (unsigned long long)i0, seed, off);
-#pragma unroll
-      for (int j = 0; j < 16; ++j) acc[j] = ((bits >> j) & 1u) ? 2.f * acc[j] : 0.f;
-    } else if (p.drop_mode == 2) {
-      float m[16];
-      unpack8(ldg16(p.mask + pix * K + i0), m);
-      unpack8(ldg16(p.mask + pix * K + i0 + 8), m + 8);
-#pragma unroll
-      for (int j = 0; j < 16; ++j) acc[j] *= m[j];
+      const unsigned long long cnt = (((base + (lane & 7)) * (unsigned long long)K + wch) >> 7) + off;
+      r = philox4x32(make_uint4((uint32_t)cnt, (uint32_t)(cnt >> 32), 0u, 0u),
+                     make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
     }
-    const uint4 q0 = pack8(acc), q1 = pack8(acc + 8);
-    uint4* o = reinterpret_cast<uint4*>(p.out + pix * K + i0);
-    o[0] = q0; o[1] = q1;
-    if (p.db) {
-      float f[16];
-      unpack8(q0, f); unpack8(q1, f + 8);
+    const bf16* g0 = p.d_head + base * 64 + c0;
+    bf16* op = p.out + base * K + i0;
+    const bf16* mp = p.mask ? p.mask + base * K + i0 : nullptr;
+#pragma unroll 1
+    for (int jp = 0; jp < 8; jp += 2, g0 += 128, op += 2 * (size_t)K) {  // two pixels per trip share the weight loads
+      if (base + jp >= p.pixels) break;                                  // (one pixel per trip: 80 registers, 3 blocks
+      const bool two = base + jp + 1 < p.pixels;                         //  per SM, but 0.111 ms against 0.093)
+      float acc[2][16];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) bsum[j] += f[j];
+      for (int j = 0; j < 16; ++j) { acc[0][j] = 0.f; acc[1][j] = 0.f; }
+      const bf16* g1 = g0 + (two ? 64 : 0);
+      for (int c = 0; c < nc; ++c) {
+        const float ga = __bfloat162float(g0[c]), gb = __bfloat162float(g1[c]);
+        const float4* w4 = ws4 + (c * 4) * tpp + t16;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 w = w4[q * tpp];
+          acc[0][4 * q] += ga * w.x; acc[0][4 * q + 1] += ga * w.y; acc[0][4 * q + 2] += ga * w.z; acc[0][4 * q + 3] += ga * w.w;
+          acc[1][4 * q] += gb * w.x; acc[1][4 * q + 1] += gb * w.y; acc[1][4 * q + 2] += gb * w.z; acc[1][4 * q + 3] += gb * w.w;
+        }
+      }
+#pragma unroll
+      for (int s2 = 0; s2 < 2; ++s2) {
+        uint32_t pk[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) pk[j] = pack_bf16x2(acc[s2][2 * j], acc[s2][2 * j + 1]);
+        if (p.drop_mode == 3) {
+          const int src = grp0 | (jp + s2);
+          const uint32_t rx = __shfl_sync(0xffffffffu, r.x, src), ry = __shfl_sync(0xffffffffu, r.y, src);
+          const uint32_t rz = __shfl_sync(0xffffffffu, r.z, src), rw = __shfl_sync(0xffffffffu, r.w, src);
+          const uint32_t w = wsel == 0 ? rx : (wsel == 1 ? ry : (wsel == 2 ? rz : rw));
+          dropout8(pk, (w >> wshift) & 0xFFFFu);
+        } else if (p.drop_mode == 2) {
+          const bf16* m = mp + (size_t)(jp + (two ? s2 : 0)) * K;
+          const uint4 m0 = ldg16(m), m1 = ldg16(m + 8);
+          const uint32_t mm[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            __nv_bfloat162 v = __hmul2(*reinterpret_cast<__nv_bfloat162*>(&pk[j]), *reinterpret_cast<const __nv_bfloat162*>(&mm[j]));
+            pk[j] = *reinterpret_cast<uint32_t*>(&v);
+          }
+        }
+        if (s2 == 0 || two) {
+          uint4* o = reinterpret_cast<uint4*>(op + (size_t)s2 * K);
+          o[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          o[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          if (p.db) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { bsum[2 * j] += bf16lo(pk[j]); bsum[2 * j + 1] += bf16hi(pk[j]); }
+          }
+        }
+      }
     }
   }
   if (p.db) {  // fold the pixel slots of the block, then one atomic per channel
@@ -581,15 +711,16 @@ int heads2_dgrad(const void* d_head, const void* wd, void* out, size_t pixels, i
   p.rng = rng; p.db = db; p.K = K; p.nh = nh; p.drop_mode = drop_mode; p.pixels = pixels;
   for (int i = 0; i < 5; ++i) p.ch_start[i] = ch_start[i];
   for (int h = 0; h < nh; ++h) if (ch_start[h + 1] - ch_start[h] > 8 || ch_start[h + 1] > 64) return DBX_ERR_ARG;
-  const int tpp = K / 16;
+  const int tpp = K / 16;                         // 32 / 64 / 96 / 128: whole warps, so the Philox shuffles stay inside a pixel
   const int threads = tpp * (256 / tpp > 0 ? 256 / tpp : 1);
-  if (threads > 256) return DBX_ERR_ARG;
+  if (threads > 256 || tpp % 32) return DBX_ERR_ARG;
   const size_t smem = (size_t)8 * K * sizeof(float);
   static SmemAttrOnce attr_once;
   { const int arc = set_max_smem_once((const void*)heads2_dgrad_kernel, 8 * 2048 * 4, &attr_once); if (arc) return arc; }
   const int ppb = threads / tpp;
-  int blocks = 4 * num_sms();
-  if ((size_t)blocks * ppb > pixels) blocks = (int)((pixels + ppb - 1) / ppb);
+  int blocks = 2 * num_sms();  // 128 registers: two 256-thread blocks per SM
+  { const char* e = ab_env("DBX_HEADS2_BLOCKS"); if (e && atoi(e) > 0) blocks = atoi(e) * num_sms(); }
+  if ((size_t)blocks * ppb * 8 > pixels) blocks = (int)((pixels + 8 * ppb - 1) / (8 * ppb));
   heads2_dgrad_kernel<<<blocks, threads, smem, st>>>(p);
   return (int)cudaGetLastError();
 }

@@ -58,6 +58,15 @@ int num_sms() {
   return n[dev];
 }
 
+static int g_tensor_sm_limit = 0;
+int set_tensor_sm_limit(int n) { const int old = g_tensor_sm_limit; g_tensor_sm_limit = n > 0 ? n : 0; return old; }
+int tensor_sms() {
+  int n = num_sms();
+  if (g_tensor_sm_limit > 0 && g_tensor_sm_limit < n) n = g_tensor_sm_limit;
+  if (n > 2) n &= ~1;  // CTA pairs
+  return n;
+}
+
 int set_max_smem_once(const void* fn, int bytes, SmemAttrOnce* s) {
   const int dev = current_device();
   if (!s->done[dev]) {
@@ -515,7 +524,7 @@ int conv_fprop(const Act& x, const void* wk, int R, int S, int pad, const Act& o
     // unit times.  Measured (tools/bench_blockn.py): conv4_2 1 081 -> 1 475 TFLOP/s, conv4_1 956 -> 1 123; on the
     // 60 x 60 maps (6.92 waves at 256) nothing changes.  128-wide units re-read the input boxes twice: +4 % cost.
     const long m_pairs = ((long)((out.W + 7) / 8) * ((out.H + 15) / 16) * out.N + 1) / 2;
-    const long pairs = num_sms() / 2 > 0 ? num_sms() / 2 : 1;
+    const long pairs = tensor_sms() / 2 > 0 ? tensor_sms() / 2 : 1;
     const long u256 = m_pairs * ((out.C + 255) / 256), u128 = m_pairs * (out.C / 128);
     const double c256 = (double)((u256 + pairs - 1) / pairs) * 256.0;
     const double c128 = (double)((u128 + pairs - 1) / pairs) * 128.0 * 1.04;
@@ -644,11 +653,11 @@ int conv_fprop(const Act& x, const void* wk, int R, int S, int pad, const Act& o
   int grid;
   if (cta2) {
     const int units = ((p.m_tiles + 1) / 2) * p.n_tiles;
-    const int pairs = num_sms() / 2;
+    const int pairs = tensor_sms() / 2;
     grid = 2 * (units < pairs ? units : pairs);
   } else {
     const int total = p.m_tiles * p.n_tiles;
-    grid = total < num_sms() ? total : num_sms();
+    grid = total < tensor_sms() ? total : tensor_sms();
   }
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = cta2 ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
@@ -904,7 +913,7 @@ int conv_wgrad(const Act& x, const Act& dy, int R, int S, int pad, float* dw, in
   { const char* e = ab_env("DBX_CTA2"); if (e && e[0] == '0') cta2 = 0; }
   const int m_units = cta2 ? (p.m_tiles + 1) / 2 : p.m_tiles;
   const int tiles = m_units * p.q_tiles;
-  const int workers = cta2 ? num_sms() / 2 : num_sms();
+  const int workers = cta2 ? tensor_sms() / 2 : tensor_sms();
   int splits = workers / tiles;
   if (splits < 1) splits = 1;
   if (splits > p.boxes_total) splits = p.boxes_total;

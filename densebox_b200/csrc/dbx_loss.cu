@@ -188,7 +188,27 @@ __global__ void __launch_bounds__(LT) loss_kernel(const LossParams p) {
 
   // ---- batch-global positive count -> negative quota (:2864-2876)
   int pos;
-  if (p.global_pos_ptr) {
+  if (p.count_slots) {
+    // every rank's count of THIS step, written by the peers' count_exchange kernels at the start of their step (long
+    // before this kernel runs); the tag (= step number) tells a stale slot from the current one
+    const int W = p.count_world;
+    const unsigned long long tag = ((const volatile unsigned long long*)p.count_slots)[2 * W];
+    double cnt = 0.0;
+    if (tid < W) {
+      const volatile unsigned long long* slot = (const volatile unsigned long long*)p.count_slots + ((tag - 1ull) & 1ull) * W + tid;
+      unsigned long long v = *slot;
+      const long long t0 = clock64();
+      while ((v >> 32) != (tag & 0xFFFFFFFFull)) {
+        if (clock64() - t0 > 20000000000LL) {  // ~10 s: a peer died
+          printf("dbx: count exchange timeout (rank slot %d, want tag %llu, have %llu)\n", tid, tag, v >> 32);
+          __trap();
+        }
+        v = *slot;
+      }
+      cnt = (double)(unsigned int)(v & 0xFFFFFFFFull);
+    }
+    pos = (int)(block_sum(cnt, red) + 0.5);
+  } else if (p.global_pos_ptr) {
     pos = *p.global_pos_ptr;
   } else if (p.global_pos >= 0) {
     pos = p.global_pos;
@@ -403,6 +423,41 @@ __global__ void count_positives_kernel(const float* __restrict__ bbox, const flo
   }
   const double tot = block_sum(cnt, red);
   if (threadIdx.x == 0) *out = (int)(tot + 0.5);
+}
+
+// One block: this shard's positives -> slot [parity][rank] of every rank's buffer, tagged with the step number.
+__global__ void count_exchange_kernel(const float* __restrict__ bbox, const float* __restrict__ labels, int B,
+                                      PeerSlots peers, unsigned long long* __restrict__ local) {
+  __shared__ double red[LT / 32];
+  __shared__ unsigned long long word;
+  double cnt = 0.0;
+  for (int i = threadIdx.x; i < B; i += LT) {
+    if (labels && labels[i] == 0.f) continue;
+    const Box s = score_box(bbox + 4 * i);
+    cnt += (double)((s.x1 - s.x0) * (s.y1 - s.y0));
+  }
+  const double tot = block_sum(cnt, red);
+  const int W = peers.world;
+  if (threadIdx.x == 0) {
+    const unsigned long long tag = local[2 * W] + 1ull;   // step number, kept on the device (CUDA-graph friendly)
+    local[2 * W] = tag;
+    word = (tag << 32) | (unsigned long long)(unsigned int)(tot + 0.5);
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < W) {
+    const unsigned long long w = word;
+    unsigned long long* dst = peers.p[threadIdx.x] + (((w >> 32) - 1ull) & 1ull) * W + peers.rank;
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(dst), "l"(w) : "memory");
+  }
+}
+
+int count_exchange(const float* bbox, const float* labels, int B, const PeerSlots& peers, unsigned long long* local,
+                   cudaStream_t st) {
+  if (!bbox || !local || B <= 0 || peers.world < 1 || peers.world > 16 || peers.rank < 0 || peers.rank >= peers.world)
+    return DBX_ERR_ARG;
+  for (int r = 0; r < peers.world; ++r) if (!peers.p[r]) return DBX_ERR_ARG;
+  count_exchange_kernel<<<1, LT, 0, st>>>(bbox, labels, B, peers, local);
+  return (int)cudaGetLastError();
 }
 
 int count_positives(const float* bbox, const float* labels, int B, int* out, cudaStream_t st) {

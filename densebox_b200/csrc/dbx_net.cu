@@ -54,7 +54,7 @@ struct Net {
   char* ws = nullptr;
   size_t ws_bytes = 0;
   size_t flat_n = 0;     // fp32 elements in the flat parameter buffer (weights then biases)
-  size_t tail_off = 0, bias_off = 0;  // first element of the conv1..conv3 filters / of the biases (see build())
+  size_t mid_off = 0, tail_off = 0, bias_off = 0;  // bucket boundaries of the flat buffers (see build())
   size_t wd_n = 0;       // bf16 elements in the dgrad-layout buffer
   bool forward_done = false, loss_done = false;
   int sgd_steps = 0;
@@ -146,14 +146,17 @@ struct Net {
       add_group("conv6_2_det", 64, 25, 64, true);
       add_group("conv6_3_det", 16, 1, 64, true);
     }
-    // Flat parameter order: the filters whose gradients are complete after backward stage 0 (conv4_1 .. heads,
-    // refine) come FIRST, then conv1_1 .. conv3_4, then every bias: gradient bucket 0 = [0, tail_off) can be
-    // all-reduced under stage 1 and everything that stage 1 finishes is ONE contiguous tail [tail_off, flat_n).
+    // Flat parameter order = completion order of the backward stages, so that every gradient bucket is one contiguous
+    // range: [0, mid_off) filters of conv4_1 .. heads (+ refine), complete after stage 0; [mid_off, tail_off) filters
+    // of the conv3 block (stage 1); [tail_off, flat_n) filters of conv1_1 .. conv2_2 and EVERY bias (stage 2).  A
+    // data-parallel caller all-reduces bucket k while stage k + 1 computes; only the last, 1 MB bucket is exposed.
     size_t off = 0, wd = 0;
-    const size_t g4 = (size_t)group_id("conv4_1");
+    const size_t g4 = (size_t)group_id("conv4_1"), g3 = (size_t)group_id("conv3_1");
     for (size_t i = g4; i < groups.size(); ++i) { groups[i].w_off = off; off += align_up((size_t)groups[i].rows * groups[i].ld, 64); }
+    mid_off = off;
+    for (size_t i = g3; i < g4; ++i) { groups[i].w_off = off; off += align_up((size_t)groups[i].rows * groups[i].ld, 64); }
     tail_off = off;
-    for (size_t i = 0; i < g4; ++i) { groups[i].w_off = off; off += align_up((size_t)groups[i].rows * groups[i].ld, 64); }
+    for (size_t i = 0; i < g3; ++i) { groups[i].w_off = off; off += align_up((size_t)groups[i].rows * groups[i].ld, 64); }
     bias_off = off;
     for (auto& g : groups) { g.b_off = off; off += align_up((size_t)g.rows, 64); }
     flat_n = off;
@@ -475,6 +478,7 @@ struct Net {
     forward_done = true;
     return DBX_OK;
   }
+  const unsigned long long* count_slots = nullptr; int count_world = 0;  // data parallel: see count_exchange
   int drop_mode = 0;  // how the last forward dropped: 0 none, 2 mask buffer, 3 Philox in place
 
   // ---- loss (+ gradients w.r.t. the head outputs)
@@ -491,6 +495,7 @@ struct Net {
     p.rand_idx = rand_idx; p.rand_stride = rand_stride; p.lm_rand_idx = lm_rand_idx;
     p.variant = variant; p.lambda_loc = lambda_loc; p.lambda_det = lambda_det; p.lambda_lm = lambda_lm;
     p.global_pos = global_pos; p.global_batch = global_batch; p.global_pos_ptr = global_pos_ptr;
+    p.count_slots = count_slots; p.count_world = count_world;
     p.clamp_lm = clamp_lm; p.B = N;
     float* sc = (float*)buf("scalars");
     p.loss = sc; p.counter = (unsigned int*)(sc + 1); p.info = (int*)(sc + 2);
@@ -504,11 +509,12 @@ struct Net {
   }
 
   // ---- backward: d_head / d_rf (bf16, written by loss() or by the caller) -> parameter gradients in g32 (+=)
-  // stage: -1 = everything; 0 = refine + heads + conv4 block (gradients of bucket 0 complete, see grad_bucket);
-  // 1 = conv3 .. conv1.  The split lets a data-parallel caller all-reduce bucket 0 while stage 1 still computes.
+  // stage: -1 = everything; 0 = refine + heads + conv4 block; 1 = conv3 block; 2 = conv2 + conv1 blocks.  After
+  // stage k the gradients of bucket k are complete (see grad_bucket): a data-parallel caller all-reduces bucket k
+  // while stage k + 1 still computes.
   int backward(cudaStream_t st, int stage = -1) {
     if (!train || !forward_done) return DBX_ERR_STATE;
-    if (stage < -1 || stage > 1) return DBX_ERR_ARG;
+    if (stage < -1 || stage > 2) return DBX_ERR_ARG;
     if (dgrad_pending) { DBX_TRY((int)cudaStreamWaitEvent(st, ev_join, 0)); dgrad_pending = false; }
     if (dgrad_stale) DBX_TRY(refresh_dgrad(st));
     // bias gradients come out of the epilogue of the launch that produces dZ (DBX_FUSE_BIAS=0: stand-alone colsum)
@@ -539,7 +545,7 @@ struct Net {
     Act d_p1 = act("d_p1", h2, w2, 64), d_a12 = act("d_a12", H, W, 64), d_a11 = act("d_a11", H, W, 64);
 
     bool heads1_bias_done = false;
-    if (stage != 1) {
+    if (stage <= 0) {
     if (variant >= 1) {
       Act rp = act("rp", h8, w8, 64), r1 = act("r1", h8 - 2, w8 - 2, 64);
       Act rup = act("rup", h4, w4, 64);
@@ -561,11 +567,11 @@ struct Net {
       const Group& g = groups[group_id("heads2")];
       if (side && !profiling) { ++launches; DBX_TRY(blockdiag_mask(G32() + g.w_off, g.rows, g.ld, nh, ch_start, side)); }
       else DBX_K("blockdiag_mask", 0.0, blockdiag_mask(G32() + g.w_off, g.rows, g.ld, nh, ch_start, st));
-      // DBX_HEADS2_DGRAD=1: streaming kernel (heads2_dgrad) instead of the K = 64 tensor-core launch.  Kept as an
-      // independent implementation for parity (tests/test_gpu_fused_bias.py); measured 0.18 ms against 0.115 ms —
-      // Philox + dropout + bias fold per element make it instruction-bound — so it is not the default.
-      bool direct = false;
-      { const char* e = ab_env("DBX_HEADS2_DGRAD"); if (e && e[0] == '1') direct = true; }
+      // The conv5_2 data gradient is a 236 MB store with <= 8 products per element: the streaming kernel (heads2_dgrad,
+      // which also yields the bias gradient of conv5_1) replaces the K = 64 tensor-core launch + the stand-alone column
+      // sums of d_hd.  DBX_HEADS2_DGRAD=0 (A/B, parity cross-check in tests/test_gpu_fused_bias.py): tensor-core path.
+      bool direct = true;
+      { const char* e = ab_env("DBX_HEADS2_DGRAD"); if (e) direct = e[0] == '1'; }
       if (direct) {
         heads1_bias_done = fuse;
         DBX_K("dgrad:heads2", 2.0 * pixels(d_head64) * macs_of("heads2"),
@@ -594,6 +600,7 @@ struct Net {
     DBX_TRY(dgrad(d_a41, "conv4_1", 3, 1, d_p3, nullptr, st));
     if (stage == 0) return join_side(st);
     }
+    if (stage == -1 || stage == 1) {
     // conv3 block: pool3 backward + the concat branch of conv3_4, then ReLU mask
     DBX_K("pool_bwd", 0.0, maxpool2x2_bwd(a34, d_p3, &d_fus_34, d_a34, st, fuse ? gb_of("conv3_4") : nullptr));
     DBX_TRY(wgrad(a32, d_a34, "conv3_4", 3, 1, st, fuse));
@@ -602,6 +609,8 @@ struct Net {
     DBX_TRY(dgrad(d_a32, "conv3_2", 3, 1, d_a31, &a31, st, fuse ? "conv3_1" : nullptr));
     DBX_TRY(wgrad(p2, d_a31, "conv3_1", 3, 1, st, fuse));
     DBX_TRY(dgrad(d_a31, "conv3_1", 3, 1, d_p2, nullptr, st));
+    if (stage == 1) return join_side(st);
+    }
     // conv2 block
     // pool2 / pool1 backward read the pooled map + the 2-bit arg-max map of the forward pass instead of a22 / a12
     if (pool_idx) DBX_K("pool_bwd", 0.0, maxpool2x2_bwd_idx(p2, d_p2, buf("pi2"), d_a22, st, fuse ? gb_of("conv2_2") : nullptr));
@@ -768,7 +777,7 @@ int dbx_net_backward(void* handle, void* stream) {
   return ((Net*)handle)->backward((cudaStream_t)stream);
 }
 int dbx_net_backward_stage(void* handle, int stage, void* stream) {
-  if (!handle || stage < 0 || stage > 1) return DBX_ERR_ARG;
+  if (!handle || stage < 0 || stage > 2) return DBX_ERR_ARG;
   return ((Net*)handle)->backward((cudaStream_t)stream, stage);
 }
 int dbx_net_join(void* handle, void* stream) {
@@ -780,16 +789,21 @@ int dbx_net_join(void* handle, void* stream) {
   }
   return DBX_OK;
 }
+int dbx_net_set_count_slots(void* handle, const void* slots, int world) {
+  if (!handle || (slots && (world < 1 || world > 16))) return DBX_ERR_ARG;
+  Net* n = (Net*)handle;
+  n->count_slots = (const unsigned long long*)slots; n->count_world = slots ? world : 0;
+  return DBX_OK;
+}
 int dbx_net_grad_bucket(void* handle, int bucket, long long* first, long long* count) {
   if (!handle || !first || !count) return DBX_ERR_ARG;
   Net* n = (Net*)handle;
   if (!n->train) return DBX_ERR_STATE;
-  const long long split = (long long)n->tail_off, bias0 = (long long)n->bias_off;
+  const long long mid = (long long)n->mid_off, tail = (long long)n->tail_off;
   switch (bucket) {
-    case 0: *first = 0; *count = split; return DBX_OK;                         // conv4_1 .. heads (+ refine) filters
-    case 1: *first = split; *count = bias0 - split; return DBX_OK;             // conv1_1 .. conv3_4 filters
-    case 2: *first = bias0; *count = (long long)n->flat_n - bias0; return DBX_OK;  // every bias
-    case 3: *first = split; *count = (long long)n->flat_n - split; return DBX_OK;  // 1 + 2: all that stage 1 completes
+    case 0: *first = 0; *count = mid; return DBX_OK;                              // conv4_1 .. heads (+ refine) filters
+    case 1: *first = mid; *count = tail - mid; return DBX_OK;                     // conv3 block filters
+    case 2: *first = tail; *count = (long long)n->flat_n - tail; return DBX_OK;   // conv1/conv2 filters + every bias
     default: return DBX_ERR_ARG;
   }
 }

@@ -215,19 +215,15 @@ class NetEngine:
         check(lib().dbx_net_backward(self.h, stream_ptr()), "net_backward")
 
     def backward_stage(self, stage):
-        """Half of backward(): 0 = refine + heads + conv4 block, 1 = conv3 .. conv1 (data-parallel overlap)."""
+        """A third of backward(): 0 = refine + heads + conv4 block, 1 = conv3 block, 2 = conv2 + conv1 blocks."""
         check(lib().dbx_net_backward_stage(self.h, c_int(stage), stream_ptr()), "net_backward_stage")
 
     def join(self):
         check(lib().dbx_net_join(self.h, stream_ptr()), "net_join")
 
-    def grad_tail(self):
-        """conv1..conv3 filters + every bias: what backward stage 1 completes, one contiguous range."""
-        return self.grad_bucket(3)
-
     def grad_bucket(self, bucket):
-        """View of g32 holding gradient bucket 0 (conv4..heads filters), 1 (conv1..conv3 filters), 2 (biases) or
-        3 (= 1 + 2, contiguous)."""
+        """View of g32 holding gradient bucket 0 (conv4..heads filters), 1 (conv3 filters) or 2 (conv1/conv2 filters
+        and every bias) — contiguous ranges, complete after backward stage 0 / 1 / 2."""
         first, count = ctypes.c_longlong(0), ctypes.c_longlong(0)
         check(lib().dbx_net_grad_bucket(self.h, c_int(bucket), ctypes.byref(first), ctypes.byref(count)),
               "net_grad_bucket")

@@ -12,8 +12,13 @@ the GPU between the input copy and the scalar loss, and the host never has to wa
 Data parallel: one process per GPU, batch sharded by rank, gradient SUM all-reduce (the loss is a sum,
 DenseBox.py:2917), and the negative quota uses the batch-GLOBAL positive count (:2864-2868) via a 1-int all-reduce.
 Both exchanges are hidden behind compute: the count all-reduce runs while the forward graph replays (only the loss
-needs it), and the backward pass is cut after the conv4 block so that the all-reduce of the conv4/heads filters
-(87 % of the gradient bytes) overlaps the conv3..conv1 half of backward; the small second bucket follows.
+needs it), and the backward pass is cut into three stages (heads + conv4 | conv3 | conv2 + conv1) whose gradient
+buckets are contiguous ranges of the flat gradient buffer: the all-reduce of bucket k runs under stage k + 1, only the
+last bucket (1 MB: conv1/conv2 filters + biases) is exposed.  The overlapped all-reduces run on a dedicated NCCL
+communicator limited to `nccl_max_ctas` CTAs, and the persistent tensor-core kernels of the overlapped stages are
+launched on `num_sms - nccl_max_ctas` SMs: a persistent kernel with a static tile schedule must be fully resident,
+otherwise the CTAs that wait for NCCL to leave their SM start late and the launch takes up to twice as long (the
+round-1 build lost 0.26 ms per step at 8 GPUs to exactly that).
 """
 import ctypes
 
@@ -46,7 +51,7 @@ class PendingLoss:
 class DenseBoxTrainer:
     def __init__(self, net, batch_size, lr=1e-9, momentum=0.9, weight_decay=5e-8, lambda_loc=3.0, lambda_det=1.0,
                  lambda_lm=0.5, patch=240, rand_width=256, process_group=None, use_cuda_graph=True, dropout=True,
-                 device=None, seed=0, allreduce_loss=False):
+                 device=None, seed=0, allreduce_loss=False, nccl_max_ctas=8, count_exchange="peer"):
         self.net = net
         self.variant = net.variant
         self.B = batch_size
@@ -56,6 +61,17 @@ class DenseBoxTrainer:
         self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
         self.rank = torch.distributed.get_rank(process_group) if process_group is not None else 0
         self.allreduce_loss = bool(allreduce_loss) and self.world > 1
+        self.pg_overlap, self.sm_reserve = self.pg, 0
+        if self.world > 1 and nccl_max_ctas and torch.distributed.get_backend(process_group) == "nccl":
+            try:  # a second communicator whose kernels occupy at most `nccl_max_ctas` SMs (ncclConfig_t.maxCTAs)
+                opts = torch.distributed.ProcessGroupNCCL.Options()
+                opts.config.max_ctas = int(nccl_max_ctas)
+                opts.config.min_ctas = 1
+                ranks = torch.distributed.get_process_group_ranks(process_group)
+                self.pg_overlap = torch.distributed.new_group(ranks=ranks, backend="nccl", pg_options=opts)
+                self.sm_reserve = (int(nccl_max_ctas) + 1) // 2 * 2
+            except Exception:  # older torch / NCCL without per-communicator config: plain overlap, no reservation
+                self.pg_overlap, self.sm_reserve = self.pg, 0
         self.dropout = dropout
         # independent dropout streams per rank (the reference's nn.Dropout draws per process): fold the rank in
         self.seed = (seed ^ (self.rank * 0x9E3779B97F4A7C15)) & 0x7FFFFFFFFFFFFFFF if self.world > 1 else seed
@@ -69,10 +85,18 @@ class DenseBoxTrainer:
             self._loss_ring = torch.zeros(LOSS_RING, device=dev)
             self._loss_host = torch.zeros(LOSS_RING, pin_memory=True)
             self._loss_events = [None] * LOSS_RING
+        # The batch-global positive count (:2864-2868) without a collective on the critical path: every rank stores
+        # its count straight into a slot of every peer's buffer (symmetric memory over NVLink, dbx_count_exchange) at
+        # the start of the step and the loss kernel sums the slots a forward pass later.  (As a 1-int NCCL all-reduce
+        # in front of the forward pass the same exchange cost 0.13 ms per step at 8 GPUs.)
+        self._slots, self._peer_ptrs = None, None
+        if self.world > 1:
+            self._setup_count_slots(count_exchange)
         self.use_graph = use_cuda_graph
         self._graphs = {}          # capture key -> CUDAGraph (single GPU: whole step) / tuple of 3 (data parallel)
         self._graph_sgd = {}       # lr -> CUDAGraph of the SGD update (data parallel: it follows the all-reduce)
         self._skip_allreduce = False   # measurement aid (bench.py: exposed-communication time); never set in training
+        self._skip_mask = 0            # measurement aid (tools/dp_probe.py): bit 0 count, 1..3 gradient buckets 0..2
         self._rng = self.eng.buffer("rng", torch.int64)
         drop_elems = self.eng.buffer("drop", torch.bfloat16).numel()
         self._rng_stride = (drop_elems + 127) // 128  # Philox calls consumed by one step
@@ -88,6 +112,28 @@ class DenseBoxTrainer:
         self._slot_ready = [None, None]   # events: H2D into the slot complete (copy stream)
         self._slot_free = [None, None]    # events: the step that read the slot has finished (compute stream)
         self.load_from_module()
+
+    def _setup_count_slots(self, mode):
+        dist, ok, t, ptrs, hdl = torch.distributed, 0, None, None, None
+        if mode == "peer" and dist.get_backend(self.pg) == "nccl":
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+                with torch.cuda.device(self.device):
+                    t = symm_mem.empty(2 * self.world + 2, dtype=torch.int64, device=self.device)
+                    t.zero_()
+                    torch.cuda.synchronize(self.device)
+                    hdl = symm_mem.rendezvous(t, group=self.pg)
+                    ptrs = [int(p) for p in hdl.buffer_ptrs]
+                ok = int(len(ptrs) == self.world and all(ptrs))
+            except Exception:
+                ok = 0
+        flag = torch.tensor([ok], device=self.device, dtype=torch.int32)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.pg)  # all ranks take the same path; also orders the zeroing
+        torch.cuda.synchronize(self.device)
+        if int(flag.item()) == 1:
+            self._slots, self._symm_hdl = t, hdl  # the handle keeps the peer mappings alive
+            self._peer_ptrs = (ctypes.c_void_p * self.world)(*ptrs)
+            check(lib().dbx_net_set_count_slots(self.eng.h, ptr(t), c_int(self.world)), "net_set_count_slots")
 
     @staticmethod
     def _new_slot(B, patch, rand_width, dev):
@@ -175,7 +221,8 @@ class DenseBoxTrainer:
         ll, ld, lm = self.lambdas
         self.eng.loss(s["bbox"], vertices=s["vertices"] if self.variant != "densebox" else None, labels=s["labels"],
                       rand_idx=s["rand"], lm_rand_idx=s["lm_rand"] if self.variant != "densebox" else None,
-                      lambda_loc=ll, lambda_det=ld, lambda_lm=lm, global_pos_dev=self.gpos if self.world > 1 else None,
+                      lambda_loc=ll, lambda_det=ld, lambda_lm=lm,
+                      global_pos_dev=self.gpos if (self.world > 1 and self._slots is None) else None,
                       global_batch=self.B * self.world if self.world > 1 else -1, clamp_lm=clamp_lm)
 
     def _forward(self, s):
@@ -205,8 +252,21 @@ class DenseBoxTrainer:
             self._graphs[key] = g  # capture does not execute: fall through to the replay
         g.replay()
 
+    def _reserved(self, fn):
+        """Run (or capture) `fn` with the tensor kernels confined to num_sms - sm_reserve SMs."""
+        if not self.sm_reserve:
+            return fn()
+        L = lib()
+        n_sm = torch.cuda.get_device_properties(self.device).multi_processor_count
+        old = L.dbx_set_tensor_sm_limit(c_int(n_sm - self.sm_reserve))
+        try:
+            return fn()
+        finally:
+            L.dbx_set_tensor_sm_limit(c_int(old))
+
     def _step_dp(self, k, clamp_lm, graph_ok):
-        """forward | loss + backward(heads, conv4) | backward(conv3..conv1) with the two exchanges overlapped."""
+        """forward | loss + backward(heads, conv4) | backward(conv3) | backward(conv2, conv1); the all-reduce of each
+        gradient bucket runs under the next stage."""
         e, dist, s = self.eng, torch.distributed, self.slots[k]
 
         def fwd():
@@ -217,7 +277,8 @@ class DenseBoxTrainer:
             self._loss(s, clamp_lm)
             e.backward_stage(0)
 
-        parts = (fwd, lb0, lambda: e.backward_stage(1))
+        parts = (fwd, lb0, lambda: self._reserved(lambda: e.backward_stage(1)),
+                 lambda: self._reserved(lambda: e.backward_stage(2)))
         key = (k, clamp_lm)
         if graph_ok and key not in self._graphs:  # capture before any collective of this step is in flight
             gs = []
@@ -227,21 +288,31 @@ class DenseBoxTrainer:
                     fn()
                 gs.append(g)
             self._graphs[key] = tuple(gs)
-        check(lib().dbx_count_positives(ptr(s["bbox"]), ptr(s["labels"]), c_int(self.B), ptr(self.gpos), stream_ptr()),
-              "count_positives")
         comm = not self._skip_allreduce
-        w_count = dist.all_reduce(self.gpos, group=self.pg, async_op=True) if comm else None
+        sk = self._skip_mask
+        if self._slots is not None:  # peer stores, no collective (runs in measurement modes too: the loss waits for it)
+            check(lib().dbx_count_exchange(ptr(s["bbox"]), ptr(s["labels"]), c_int(self.B), self._peer_ptrs,
+                                           c_int(self.world), c_int(self.rank), ptr(self._slots), stream_ptr()),
+                  "count_exchange")
+        else:
+            check(lib().dbx_count_positives(ptr(s["bbox"]), ptr(s["labels"]), c_int(self.B), ptr(self.gpos),
+                                            stream_ptr()), "count_positives")
+            # The fallback exchange completes BEFORE the forward pass starts: overlapped with it, the NCCL kernel takes
+            # SMs at some kernel boundary and the next persistent convolution, launched on all SMs, waits for them.
+            if comm and not sk & 1:
+                dist.all_reduce(self.gpos, group=self.pg_overlap, async_op=True).wait()
         run = [g.replay for g in self._graphs[key]] if graph_ok else parts
         run[0]()
-        if w_count is not None:
-            w_count.wait()
         run[1]()
         works = []
-        if comm:
-            works.append(dist.all_reduce(e.grad_bucket(0), group=self.pg, async_op=True))  # SUM: the loss is a sum (:2917)
+        if comm and not sk & 2:  # SUM: the loss is a sum (:2917)
+            works.append(dist.all_reduce(e.grad_bucket(0), group=self.pg_overlap, async_op=True))
         run[2]()
-        if comm:
-            works.append(dist.all_reduce(e.grad_tail(), group=self.pg, async_op=True))  # conv1..conv3 filters + biases
+        if comm and not sk & 4:
+            works.append(dist.all_reduce(e.grad_bucket(1), group=self.pg_overlap, async_op=True))
+        run[3]()
+        if comm and not sk & 8:
+            works.append(dist.all_reduce(e.grad_bucket(2), group=self.pg, async_op=True))  # exposed: full-speed group
         for w in works:
             w.wait()
         if graph_ok:

@@ -96,6 +96,16 @@ int dbx_loss_maps(const float* const* maps, const long* strides, float* const* g
                   float* loss, int* info, unsigned char* mask_out, unsigned char* lm_mask_out, void* stream);
 /* Positive pixels of a label shard (sum of the clipped init_score_map boxes, DenseBox.py:2864) -> *out (device). */
 int dbx_count_positives(const float* bbox, const float* labels, int B, int* out, void* stream);
+/* The same count exchanged WITHOUT a collective (data parallel): every rank owns a slot buffer of
+ * 2 * world + 1 unsigned 64-bit words in peer-accessible memory (zeroed before first use; peer_slots[r] = rank r's
+ * buffer as mapped into this process, HOST array of device pointers; local_slots = this rank's own).  The kernel
+ * writes (step << 32 | count) into slot [step & 1][rank] of every rank with system-scope stores over NVLink and keeps
+ * the step counter in word [2 * world] of the local buffer.  dbx_net_set_count_slots(handle, local_slots, world) makes
+ * dbx_net_loss sum the slots of the current step (it spins until every rank's word carries the step's tag — they
+ * were written a forward pass earlier) instead of reading global_pos / global_pos_ptr. */
+int dbx_count_exchange(const float* bbox, const float* labels, int B, void* const* peer_slots, int world, int rank,
+                       void* local_slots, void* stream);
+int dbx_net_set_count_slots(void* handle, const void* slots, int world);
 /* nn.Dropout(p=0.5) keep-mask x2 as an explicit bf16 tensor — the same Philox4x32-10 bits the conv epilogues draw
  * in place for dropout_mode 1/3 (element e: bit e&127 of philox(counter (e>>7)+offset, key seed)); n % 16 == 0. */
 int dbx_dropout_mask(void* mask, unsigned long long n, unsigned long long seed, unsigned long long offset,
@@ -165,16 +175,22 @@ int dbx_net_loss(void* handle, const float* bbox, const float* vertices, const f
 
 /* loss.backward() — DenseBox.py:2925: consumes "d_head"/"d_rf", accumulates (+=) parameter gradients into "g32". */
 int dbx_net_backward(void* handle, void* stream);
-/* The same backward pass in two halves for data-parallel callers (the reference is single-device, the
- * autograd graph of :2925 is simply cut after conv4_1): stage 0 = refine branch + heads + conv4 block, stage 1 =
- * conv3 .. conv1.  After stage 0 the gradients of bucket 0 are final, so their all-reduce overlaps stage 1.
+/* The same backward pass in three stages for data-parallel callers (the reference is single-device, the
+ * autograd graph of :2925 is simply cut after conv4_1 and after conv3_1): stage 0 = refine branch + heads + conv4 block,
+ * 1 = conv3 block, 2 = conv2 + conv1 blocks.  After stage k the gradients of bucket k are final, so the all-reduce of
+ * bucket k overlaps stage k + 1 and only the last (1 MB) bucket is exposed.
  * dbx_net_grad_bucket: element range [first, first+count) of "g32" — bucket 0 = filters conv4_1..heads(+refine),
- * 1 = filters conv1_1..conv3_4, 2 = every bias, 3 = buckets 1 and 2 together (contiguous: one all-reduce for
- * everything stage 1 completes).  dbx_net_join: make `stream` wait for the filter re-layout that
- * dbx_net_forward forked onto the engine's side stream (needed when forward is captured into its own CUDA graph). */
+ * 1 = filters of the conv3 block, 2 = filters conv1_1..conv2_2 + every bias (the flat buffers are laid out in this
+ * order).  dbx_net_join: make `stream` wait for the filter re-layout that dbx_net_forward forked onto the engine's
+ * side stream (needed when forward is captured into its own CUDA graph).
+ * dbx_set_tensor_sm_limit: the persistent tcgen05 kernels launched from now on use at most n SMs (0 = all) — a
+ * data-parallel caller leaves a few SMs to the NCCL kernel whose all-reduce overlaps the stage (a persistent kernel
+ * with a static tile schedule must be fully resident: if NCCL's CTAs hold SMs it counted on, its last CTAs start
+ * late and the whole launch takes up to twice as long).  Returns the previous limit. */
 int dbx_net_backward_stage(void* handle, int stage, void* stream);
 int dbx_net_grad_bucket(void* handle, int bucket, long long* first, long long* count);
 int dbx_net_join(void* handle, void* stream);
+int dbx_set_tensor_sm_limit(int n);
 int dbx_net_zero_grad(void* handle, void* stream);                       /* optimizer.zero_grad() :2858 */
 /* optimizer.step() — torch.optim.SGD(momentum, weight_decay) :2821-2824, :2926; also clears g32 and refreshes the
  * bf16 filters. */
