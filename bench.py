@@ -15,7 +15,7 @@ Further records on the same JSON line (driver-run evidence for the other BASELIN
   N = 1 : parity (loss of the first bench batch vs the CPU oracle fed the same Philox dropout mask), config3 (B=64
           DenseBoxLM), config5 (1024x1024 B=16 DenseBoxLMLOC inference + top-10 decode + NMS, images/s), sustained
           (>= 300 steps of the headline workload with its own clock record), dropin (the nn.Module path: net(x) ->
-          densebox_loss -> backward -> torch.optim.SGD.step)
+          densebox_loss -> backward -> torch.optim.SGD.step), e2e_u8 (the headline step fed uint8 image bytes)
   N > 1 : config4 (DenseBoxLM, 32 per GPU, data parallel: value, the same variant on one GPU of this box, exposed
           communication per step = step time with minus without the all-reduces)
 `--impl reference` times the reference's CPU implementation of the same step (the oracle port — the reference is
@@ -343,6 +343,28 @@ def kernel_profile(tr, variant, B, ms_step, pk):
     return roof, kern
 
 
+def run_e2e_u8(c, B=32, steps=20):
+    """The headline workload fed as decoded image bytes (uint8 NHWC): ToTensor + Normalize fused into the first kernel,
+    a quarter of the host->device bytes."""
+    import numpy as np
+    import torch
+    import densebox_b200
+    net = make_net("densebox", c.dev)
+    tr = densebox_b200.DenseBoxTrainer(net, B, lr=1e-9, momentum=0.9, weight_decay=5e-8, dropout=True, device=c.dev,
+                                       input_u8=True)
+    g = torch.Generator().manual_seed(9)
+    base = synth("densebox", B, 0, 4)
+    batches = [dict(b, x=torch.randint(0, 256, (B, 240, 240, 3), generator=g, dtype=torch.uint8).pin_memory()) for b in base]
+    for i in range(5):
+        b = batches[i % 4]
+        tr.step(b["x"], b["bbox"], rand_neg_idx=b["rand"])
+    ms, loss, _ = timed_steps(c, tr, batches, steps, host=True)
+    h2d = sum(v.numel() * v.element_size() for v in batches[0].values())
+    return {"value": round(B / (ms * 1e-3), 1), "unit": "patches/s", "ms_per_step": round(ms, 4), "h2d_bytes_per_step": h2d,
+            "d2h_bytes_per_step": 4, "loss": loss,
+            "input": "uint8 [B,240,240,3] pinned host batches; ToTensor + Normalize(ImageNet) inside im2col3x3_c3_u8_kernel"}
+
+
 def run_training(c, variant, B, steps, warmup, pg, graph=True, parity=False, profile=False, e2e=True, exposed=False):
     """One trainer, one workload: returns the record (rank 0 fills everything, other ranks a subset)."""
     import torch
@@ -560,6 +582,8 @@ def main():
         records["config5"] = run_inference(c)
         torch.cuda.empty_cache()
         records["dropin"] = run_dropin(c)
+        torch.cuda.empty_cache()
+        records["e2e_u8"] = run_e2e_u8(c, steps=args.steps)
         torch.cuda.empty_cache()
     if full and world > 1:
         r4 = run_training(c, "lm", 32, args.steps, args.warmup, pg, graph=not args.no_graph, e2e=True, exposed=True)

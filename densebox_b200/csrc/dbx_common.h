@@ -87,6 +87,7 @@ int conv_wgrad(const Act& x, const Act& dy, int R, int S, int pad, float* dw, in
 
 // ---- HBM-bound kernels (dbx_elementwise.cu)
 int im2col3x3_c3(const float* x, void* out, int N, int H, int W, int mode, cudaStream_t st);  // mode 2: pairs layout
+int im2col3x3_c3_u8(const unsigned char* x, const float* lut, void* out, int N, int H, int W, int mode, cudaStream_t st);
 int conv1_1_fold_pairs(const float* scratch, float* gw, float* gb, cudaStream_t st);
 // idx (optional): u16 per (pooled pixel, 8-channel vector), 2 bits per element = position of the first maximum
 int maxpool2x2_fwd(const Act& y, const Act& o, cudaStream_t st, void* idx = nullptr);

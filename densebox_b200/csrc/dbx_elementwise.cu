@@ -63,6 +63,52 @@ __global__ void im2col3x3_c3_kernel(const float* __restrict__ x, bf16* __restric
   }
 }
 
+// The same ingest from the decoded image bytes: X uint8 NHWC [N,H,W,3] (what PIL hands over), ToTensor + Normalize
+// (DenseBox.py:766-772) applied through a 3 x 256 fp32 table built on the host with torchvision's own arithmetic
+// (densebox_b200/data.py::ingest_table), so the result is bit-identical to normalising on the host and calling the
+// fp32 kernel — and the batch crosses PCIe as 3 bytes per pixel instead of 12.
+__global__ void im2col3x3_c3_u8_kernel(const unsigned char* __restrict__ x, const float* __restrict__ lut,
+                                       bf16* __restrict__ out, int N, int H, int W, int mode) {
+  __shared__ float tab[3 * 256];
+  for (int i = threadIdx.x; i < 3 * 256; i += blockDim.x) tab[i] = lut[i];
+  __syncthreads();
+  const size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= (size_t)N * H * W) return;
+  const int xw = (int)(pix % W), y = (int)((pix / W) % H), n = (int)(pix / ((size_t)W * H));
+  float f[32];
+#pragma unroll
+  for (int k = 27; k < 32; ++k) f[k] = 0.f;
+  const unsigned char* xn = x + (size_t)n * H * W * 3;
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const int yy = y + r - 1;
+    const bool yok = yy >= 0 && yy < H;
+#pragma unroll
+    for (int s = 0; s < 3; ++s) {
+      const int xx = xw + s - 1;
+      const bool ok = yok && xx >= 0 && xx < W;
+      const unsigned char* px = xn + ((size_t)yy * W + xx) * 3;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) f[(r * 3 + s) * 3 + c] = ok ? tab[c * 256 + __ldg(px + c)] : 0.f;
+    }
+  }
+  if (mode == 2) f[27] = 1.f;
+  uint4* o = reinterpret_cast<uint4*>(out + pix * (mode == 2 ? 32 : 64));
+#pragma unroll
+  for (int q = 0; q < 4; ++q) o[q] = pack8(f + 8 * q);
+  if (mode == 1) {
+#pragma unroll
+    for (int q = 4; q < 8; ++q) o[q] = make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+
+int im2col3x3_c3_u8(const unsigned char* x, const float* lut, void* out, int N, int H, int W, int mode, cudaStream_t st) {
+  if (!x || !lut || !out || mode < 0 || mode > 2 || (mode == 2 && (W & 1))) return DBX_ERR_ARG;
+  const size_t total = (size_t)N * H * W;
+  im2col3x3_c3_u8_kernel<<<grid_for(total, 128), 128, 0, st>>>(x, lut, (bf16*)out, N, H, W, mode);
+  return (int)cudaGetLastError();
+}
+
 // mode 0: channels 32..63 are left untouched (the engine zeroes them once at creation); 1: written; 2: pairs layout.
 int im2col3x3_c3(const float* x, void* out, int N, int H, int W, int mode, cudaStream_t st) {
   if (!x || !out || mode < 0 || mode > 2 || (mode == 2 && (W & 1))) return DBX_ERR_ARG;

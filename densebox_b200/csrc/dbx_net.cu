@@ -410,8 +410,11 @@ struct Net {
   // by the {0,2} bf16 mask the caller wrote into `drop`; 3 = like 1 but (seed, offset) are read from the `rng`
   // region as the caller left it (CUDA-graph replays: update the region between replays).
   unsigned long long rng_host[2] = {0, 0};
-  int forward(const float* x, int dropout_mode, unsigned long long seed, unsigned long long offset, cudaStream_t st) {
-    if (!x) return DBX_ERR_ARG;
+  // x_u8 != null: the batch as decoded image bytes (uint8 NHWC) + the 3 x 256 ToTensor/Normalize table (see
+  // im2col3x3_c3_u8); otherwise x = fp32 NCHW, already normalised (the reference's forward argument).
+  int forward(const float* x, int dropout_mode, unsigned long long seed, unsigned long long offset, cudaStream_t st,
+              const unsigned char* x_u8 = nullptr, const float* lut = nullptr) {
+    if (!x && !(x_u8 && lut)) return DBX_ERR_ARG;
     if (dropout_mode < 0 || dropout_mode > 3) return DBX_ERR_ARG;
     if (dropout_mode && !train) return DBX_ERR_STATE;
     const int h2 = H / 2, w2 = W / 2, h4 = H / 4, w4 = W / 4, h8 = H / 8, w8 = W / 8;
@@ -430,7 +433,8 @@ struct Net {
       DBX_TRY((int)cudaEventRecord(ev_join, side));
       dgrad_pending = true;
     }
-    DBX_K("im2col", 0.0, im2col3x3_c3(x, col0.ptr, N, H, W, pairs ? 2 : 0, st));
+    if (x_u8) DBX_K("im2col", 0.0, im2col3x3_c3_u8(x_u8, lut, col0.ptr, N, H, W, pairs ? 2 : 0, st));
+    else DBX_K("im2col", 0.0, im2col3x3_c3(x, col0.ptr, N, H, W, pairs ? 2 : 0, st));
     if (pairs) {
       Act col0p = act("col0", H, W / 2, 64), a11p = act("a11", H, W / 2, 128);
       ConvEpilogue e;
@@ -761,6 +765,11 @@ int dbx_net_forward(void* handle, const float* x, int dropout_mode, unsigned lon
                     unsigned long long offset, void* stream) {
   if (!handle) return DBX_ERR_ARG;
   return ((Net*)handle)->forward(x, dropout_mode, seed, offset, (cudaStream_t)stream);
+}
+int dbx_net_forward_u8(void* handle, const unsigned char* x_u8, const float* table, int dropout_mode,
+                       unsigned long long seed, unsigned long long offset, void* stream) {
+  if (!handle || !x_u8 || !table) return DBX_ERR_ARG;
+  return ((Net*)handle)->forward(nullptr, dropout_mode, seed, offset, (cudaStream_t)stream, x_u8, table);
 }
 int dbx_net_loss(void* handle, const float* bbox, const float* vertices, const float* labels,
                  const long long* rand_idx, int rand_stride, const long long* lm_rand_idx, float lambda_loc,

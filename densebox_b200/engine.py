@@ -129,48 +129,54 @@ class NetEngine:
     # ---- all parameters of a module in one launch (dbx_net_xfer_params)
     def _xfer(self, mode, triples, what):
         n = len(triples)
-        names = (ctypes.c_char_p * n)(*[t[0].encode() for t in triples])
-        wp = (ctypes.c_void_p * n)(*[t[1].data_ptr() for t in triples])
-        bp = (ctypes.c_void_p * n)(*[t[2].data_ptr() for t in triples])
-        ws = (ctypes.c_long * (4 * n))()
-        bs = (ctypes.c_long * n)()
+        if getattr(self, "_xfer_names", None) is None or len(self._xfer_names) != n:
+            self._xfer_names = (ctypes.c_char_p * n)(*[t[0].encode() for t in triples])
+            self._xfer_wp, self._xfer_bp = (ctypes.c_void_p * n)(), (ctypes.c_void_p * n)()
+            self._xfer_ws, self._xfer_bs = (ctypes.c_long * (4 * n))(), (ctypes.c_long * n)()
+        wp, bp, ws, bs = self._xfer_wp, self._xfer_bp, self._xfer_ws, self._xfer_bs
         for i, (_, w, b) in enumerate(triples):
             assert w.dtype == torch.float32 and b.dtype == torch.float32 and w.is_cuda and b.is_cuda
-            st = list(w.stride()) + [0, 0, 0]
-            ws[4 * i:4 * i + 4] = st[:4]
+            wp[i], bp[i] = w.data_ptr(), b.data_ptr()
+            st = w.stride()
+            for k in range(4):
+                ws[4 * i + k] = st[k] if k < len(st) else 0
             bs[i] = b.stride(0)
-        check(lib().dbx_net_xfer_params(self.h, c_int(mode), c_int(n), names, wp, ws, bp, bs, stream_ptr()), what)
+        check(lib().dbx_net_xfer_params(self.h, c_int(mode), c_int(n), self._xfer_names, wp, ws, bp, bs, stream_ptr()),
+              what)
+
+    def _param_triples(self, module, device=None):
+        out = []
+        for name in unique_param_names(self.variant):
+            w, b = module._wb(name)
+            w, b = w.detach(), b.detach()
+            if device is not None and w.device != device:
+                w, b = w.to(device), b.to(device)
+            out.append((name, w, b))
+        return out
 
     def set_params(self, module, device=None):
         """Pack every (weight, bias) the variant uses from a drop-in module (or any object with `_wb(name)`)."""
-        dev = self.device if device is None else device
-        triples = []
-        for name in unique_param_names(self.variant):
-            w, b = module._wb(name)
-            triples.append((name, w.detach().to(dev), b.detach().to(dev)))
-        self._xfer(0, triples, "xfer_params(set)")
+        self._xfer(0, self._param_triples(module, self.device if device is None else device), "xfer_params(set)")
         self._dgrad_fresh = False
 
     def get_params(self, module):
         """Write the engine's fp32 master weights back into the module's parameters (in place)."""
-        triples = []
-        for name in unique_param_names(self.variant):
-            w, b = module._wb(name)
-            triples.append((name, w.detach(), b.detach()))
-        self._xfer(1, triples, "xfer_params(get)")
+        self._xfer(1, self._param_triples(module), "xfer_params(get)")
         if hasattr(module, "_param_epoch"):
             module._param_epoch += 1  # raw in-place writes do not bump torch's version counters
 
     def get_grads(self, module):
-        """Fresh fp32 tensors shaped like the module's parameters holding the engine's gradients: [w0, b0, w1, ...]."""
-        triples, out = [], []
+        """Fresh fp32 tensors shaped like the module's parameters holding the engine's gradients: [w0, b0, w1, ...]
+        (views of ONE flat allocation: a single allocator call per backward instead of one per tensor)."""
+        shapes = []
         for name in unique_param_names(self.variant):
             w, b = module._wb(name)
-            gw = torch.empty_like(w, memory_format=torch.contiguous_format)
-            gb = torch.empty_like(b)
-            triples.append((name, gw, gb))
-            out += [gw, gb]
-        self._xfer(2, triples, "xfer_params(grads)")
+            shapes += [w.shape, b.shape]
+        sizes = [s.numel() for s in shapes]
+        flat = torch.empty(sum(sizes), dtype=torch.float32, device=self.device)
+        out = [t.view(s) for t, s in zip(flat.split(sizes), shapes)]
+        names = unique_param_names(self.variant)
+        self._xfer(2, [(names[i], out[2 * i], out[2 * i + 1]) for i in range(len(names))], "xfer_params(grads)")
         return out
 
     def get_outputs(self, want):
@@ -191,11 +197,26 @@ class NetEngine:
                                              stream_ptr()), "net_set_output_grads")
 
     # ---- the path
+    def set_ingest(self, mean=None, std=None):
+        """ToTensor + Normalize table for uint8 inputs (densebox_b200.data.ingest_table); default: ImageNet statistics."""
+        from .data import IMAGENET_MEAN, IMAGENET_STD, ingest_table
+        self._lut = ingest_table(mean or IMAGENET_MEAN, std or IMAGENET_STD).to(self.device)
+
     def forward(self, x, dropout_mode=0, seed=0, offset=0):
-        assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()
-        assert tuple(x.shape) == (self.N, 3, self.H, self.W), (tuple(x.shape), (self.N, 3, self.H, self.W))
-        check(lib().dbx_net_forward(self.h, ptr(x), c_int(dropout_mode), c_ull(seed), c_ull(offset), stream_ptr()),
-              "net_forward")
+        """x: fp32 [N,3,H,W], normalised (the reference's forward argument) — or uint8 [N,H,W,3], the decoded image
+        bytes, normalised inside the first kernel (dbx_net_forward_u8)."""
+        assert x.is_cuda and x.is_contiguous()
+        if x.dtype == torch.uint8:
+            assert tuple(x.shape) == (self.N, self.H, self.W, 3), (tuple(x.shape), (self.N, self.H, self.W, 3))
+            if getattr(self, "_lut", None) is None:
+                self.set_ingest()
+            check(lib().dbx_net_forward_u8(self.h, ptr(x), ptr(self._lut), c_int(dropout_mode), c_ull(seed),
+                                           c_ull(offset), stream_ptr()), "net_forward_u8")
+        else:
+            assert x.dtype == torch.float32
+            assert tuple(x.shape) == (self.N, 3, self.H, self.W), (tuple(x.shape), (self.N, 3, self.H, self.W))
+            check(lib().dbx_net_forward(self.h, ptr(x), c_int(dropout_mode), c_ull(seed), c_ull(offset), stream_ptr()),
+                  "net_forward")
         self.generation += 1
 
     def loss(self, bbox, vertices=None, labels=None, rand_idx=None, lm_rand_idx=None, lambda_loc=3.0, lambda_det=1.0,

@@ -51,7 +51,11 @@ class PendingLoss:
 class DenseBoxTrainer:
     def __init__(self, net, batch_size, lr=1e-9, momentum=0.9, weight_decay=5e-8, lambda_loc=3.0, lambda_det=1.0,
                  lambda_lm=0.5, patch=240, rand_width=256, process_group=None, use_cuda_graph=True, dropout=True,
-                 device=None, seed=0, allreduce_loss=False, nccl_max_ctas=8, count_exchange="peer"):
+                 device=None, seed=0, allreduce_loss=False, nccl_max_ctas=8, count_exchange="peer", input_u8=False,
+                 mean=None, std=None):
+        """input_u8=True: `step()` / `prefetch()` take the batch as decoded image bytes, uint8 [B,patch,patch,3]
+        (densebox_b200.data.load_patch_u8), and ToTensor + Normalize(mean, std) (DenseBox.py:766-772) happen inside
+        the first kernel — a quarter of the host->device bytes of the fp32 [B,3,patch,patch] form."""
         self.net = net
         self.variant = net.variant
         self.B = batch_size
@@ -80,7 +84,9 @@ class DenseBoxTrainer:
         self.eng = NetEngine(self.variant, batch_size, patch, patch, train=True, device=self.device)
         dev = self.device
         with torch.cuda.device(dev):
-            self.slots = [self._new_slot(batch_size, patch, rand_width, dev) for _ in range(2)]
+            self.slots = [self._new_slot(batch_size, patch, rand_width, dev, input_u8) for _ in range(2)]
+            if input_u8:
+                self.eng.set_ingest(mean, std)
             self.gpos = torch.zeros(1, dtype=torch.int32, device=dev)
             self._loss_ring = torch.zeros(LOSS_RING, device=dev)
             self._loss_host = torch.zeros(LOSS_RING, pin_memory=True)
@@ -136,8 +142,10 @@ class DenseBoxTrainer:
             check(lib().dbx_net_set_count_slots(self.eng.h, ptr(t), c_int(self.world)), "net_set_count_slots")
 
     @staticmethod
-    def _new_slot(B, patch, rand_width, dev):
-        return {"x": torch.zeros(B, 3, patch, patch, device=dev), "bbox": torch.zeros(B, 4, device=dev),
+    def _new_slot(B, patch, rand_width, dev, input_u8=False):
+        x = (torch.zeros(B, patch, patch, 3, dtype=torch.uint8, device=dev) if input_u8
+             else torch.zeros(B, 3, patch, patch, device=dev))
+        return {"x": x, "bbox": torch.zeros(B, 4, device=dev),
                 "vertices": torch.zeros(B, 8, device=dev), "labels": torch.ones(B, device=dev),
                 "rand": torch.zeros(B, rand_width, dtype=torch.int64, device=dev),
                 "lm_rand": torch.zeros(B, 4, dtype=torch.int64, device=dev), "labels_are_ones": True}

@@ -158,6 +158,13 @@ int dbx_net_refresh_dgrad(void* handle, void* stream);
 int dbx_net_forward(void* handle, const float* x, int dropout_mode, unsigned long long seed,
                     unsigned long long offset, void* stream);
 
+/* The same forward pass fed by the callers' side of the path: x_u8 = the decoded image bytes, uint8
+ * NHWC [N,H,W,3]; table = fp32 [3][256], table[c][u] = ToTensor + Normalize of byte u in channel c (DenseBox.py:766-772,
+ * :3609-3621; densebox_b200.data.ingest_table builds it with torchvision's float32 arithmetic).  The lookup is fused
+ * into the im2col kernel of conv1_1: bit-identical to normalising on the host, a quarter of the host->device bytes. */
+int dbx_net_forward_u8(void* handle, const unsigned char* x_u8, const float* table, int dropout_mode,
+                       unsigned long long seed, unsigned long long offset, void* stream);
+
 /* The loop body between forward and backward — DenseBox.py:2843-2918 (variant 0), :2575-2723 (1), :2300-2456 and
  * :2023-2180 (2, `labels` != NULL selects the pos/neg-patch `_pn` helpers).  Inputs are device pointers:
  * bbox [N,4] / vertices [N,8] in 60-space floats, labels [N] (or NULL), rand_idx [N,rand_stride] int64 = the

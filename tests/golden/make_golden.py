@@ -10,6 +10,8 @@ The reference ships no tests or golden vectors, so the oracle is
                      with the reference's own helper functions on random head maps (np.random.choice draws injected)
   * forward_*.npz  — DenseBox / DenseBoxLM / DenseBoxLMLOC modules of the reference on the seeded KAT input
   * decode_nms.npz — parse_out_MN / parse_DetLMLOC / parse_DetLM / NMS
+  * ingest.npz     — file-name label parsers of DenseBoxDataset / LPPatchLM_Online / LPPatch_Online and the default
+                     Resize + CenterCrop + ToTensor + Normalize transform on a random image
   * state_dict.npz — key -> shape of the three modules' state_dict() and the outcome of a strict load_state_dict round
                      trip between the reference modules and the drop-in modules (both directions)
 Loading shims: matplotlib stub, CUDA hidden during import, float64 labels for the loc-map
@@ -250,8 +252,50 @@ def gen_state_dict(REF):
     np.savez_compressed(os.path.join(HERE, "state_dict.npz"), **d)
 
 
+def gen_ingest(REF):
+    """Callers' side (f-3): the file-name label parsers of the three online datasets and the default transform
+    (Resize + CenterCrop to the stored size, ToTensor, Normalize) of DenseBoxDataset on a random RGB image."""
+    import tempfile
+    from PIL import Image
+    rs = np.random.RandomState(13)
+    names12 = []
+    for i in range(24):
+        v = rs.randint(1, 240, 12)
+        names12.append("img%03d_label_%s.jpg" % (i, "_".join(str(int(x)) for x in v)))
+    names12 += ["neg_7_label_0_0_0_0_0_0_0_0_0_0_0_0.jpg", "a_b_label_1_2_3_4_5_6_7_8_9_10_11_12_x.png"]
+    names4 = ["p%02d_label_%d_%d_%d_%d.jpg" % (i, *rs.randint(1, 240, 4)) for i in range(12)]
+    d = {}
+    with tempfile.TemporaryDirectory() as root:
+        r12, r4 = os.path.join(root, "a"), os.path.join(root, "b")
+        os.makedirs(r12); os.makedirs(r4)
+        for n in names12:
+            open(os.path.join(r12, n), "wb").close()
+        for n in names4:
+            open(os.path.join(r4, n), "wb").close()
+        ds = REF.DenseBoxDataset(r12, transform=None, size=(48, 64))
+        d["db_names"] = np.array([os.path.split(p)[1] for p in ds.imgs_path])
+        d["db_bbox"] = torch.stack(ds.bboxes).numpy(); d["db_vertices"] = torch.stack(ds.vertices).numpy()
+        d["db_labels"] = torch.stack(ds.labels).numpy().reshape(-1)
+        lm_names = [n for n in names12 if not n.startswith("neg")]
+        r12b = os.path.join(root, "c"); os.makedirs(r12b)
+        for n in lm_names:
+            open(os.path.join(r12b, n), "wb").close()
+        dl = REF.LPPatchLM_Online(r12b, transform=None, size=(48, 64))
+        d["lm_names"] = np.array([os.path.split(p)[1] for p in dl.imgs_path])
+        d["lm_bbox"] = torch.stack(dl.bboxes).numpy(); d["lm_vertices"] = torch.stack(dl.vertices).numpy()
+        d4 = REF.LPPatch_Online(r4, transform=None, size=(48, 64))
+        d["b_names"] = np.array([os.path.split(p)[1] for p in d4.imgs_path])
+        d["b_bbox"] = torch.stack(d4.labels).numpy()
+        img = rs.randint(0, 256, (48, 64, 3)).astype(np.uint8)
+        img[0, 0] = (0, 0, 0); img[0, 1] = (255, 255, 255)
+        d["img_u8"] = img
+        d["img_norm"] = ds.transform(Image.fromarray(img)).numpy()   # the reference's own Compose
+    np.savez_compressed(os.path.join(HERE, "ingest.npz"), **d)
+
+
 if __name__ == "__main__":
     REF = load_reference()
+    gen_ingest(REF)
     gen_state_dict(REF)
     gen_geometry(REF)
     gen_loss(REF)

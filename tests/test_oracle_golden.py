@@ -144,3 +144,25 @@ def test_state_dict_shapes_and_checkpoint_round_trip():
         got = O.forward(O.params_from_state_dict(ours.state_dict(), "lm"), x, "lm")
     for a, b in zip(got, want):
         np.testing.assert_allclose(a.numpy(), b.numpy(), rtol=1e-4, atol=1e-4)
+
+
+def test_label_parser_and_ingest_table_match_reference_datasets():
+    """f-3, callers' side: densebox_b200.data against the reference's datasets (fixture written by make_golden.py from
+    DenseBoxDataset / LPPatchLM_Online / LPPatch_Online and DenseBoxDataset's default transform): labels bit-exact,
+    the ToTensor + Normalize table bit-exact on every byte value that occurs."""
+    from densebox_b200 import data
+    d = np.load(os.path.join(G, "ingest.npz"))
+    lab, bbox, verts = data.parse_label_names([str(n) for n in d["db_names"]], kind="densebox")
+    assert np.array_equal(lab.numpy(), d["db_labels"]) and (lab == 0).sum() == 1
+    assert np.array_equal(bbox.numpy(), d["db_bbox"]) and np.array_equal(verts.numpy(), d["db_vertices"])
+    _, bbox, verts = data.parse_label_names([str(n) for n in d["lm_names"]], kind="lm")
+    assert np.array_equal(bbox.numpy(), d["lm_bbox"]) and np.array_equal(verts.numpy(), d["lm_vertices"])
+    _, bbox, _ = data.parse_label_names([str(n) for n in d["b_names"]], kind="bbox")
+    assert np.array_equal(bbox.numpy(), d["b_bbox"])
+    with pytest.raises(ValueError):
+        data.parse_label_name("no_label_here.jpg")
+    u8 = torch.from_numpy(d["img_u8"])
+    tab = data.ingest_table()
+    via_table = torch.stack([tab[c][u8[..., c].long()] for c in range(3)])
+    assert torch.equal(via_table, torch.from_numpy(d["img_norm"]))
+    assert torch.equal(data.normalize_u8(u8[None])[0], torch.from_numpy(d["img_norm"]))
