@@ -24,7 +24,7 @@ def __getattr__(name):  # lazy: importing the package must not need torch/CUDA (
     if name in ("parse_label_name", "parse_label_names", "load_patch_u8", "ingest_table", "normalize_u8"):
         from . import data
         return getattr(data, name)
-    if name in ("decode_nms",):
+    if name in ("decode_nms", "perspective_transform", "perspective_matrix"):
         from . import postproc
         return getattr(postproc, name)
     raise AttributeError(name)

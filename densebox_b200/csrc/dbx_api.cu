@@ -160,4 +160,9 @@ int dbx_decode_nms_heat(const float* score, long s_img, long s_pix, const float*
                     dets, keep, (cudaStream_t)stream, 1);
 }
 
+int dbx_warp_perspective_u8(const unsigned char* src, int H, int W, int C, const double* minv, unsigned char* dst,
+                            int dH, int dW, void* stream) {
+  return warp_perspective_u8(src, H, W, C, minv, dst, dH, dW, (cudaStream_t)stream);
+}
+
 }  // extern "C"

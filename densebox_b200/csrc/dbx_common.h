@@ -198,4 +198,8 @@ int decode_nms(const float* score, long s_img, long s_pix, const float* loc, lon
                const float* lmloc, long m_img, long m_pix, long m_ch, int N, int H4, int W4, int K, double thresh,
                float* dets, int* keep, cudaStream_t st, int lm_heat = 0);  // lm_heat: `lmloc` = 4 heat-maps (parse_DetLM)
 
+// cv2.warpPerspective(INTER_LINEAR, constant border) on uint8 HWC images; minv = 3 x 3 inverse map (HOST pointer)
+int warp_perspective_u8(const unsigned char* src, int H, int W, int C, const double* minv, unsigned char* dst, int dH,
+                        int dW, cudaStream_t st);
+
 }  // namespace dbx

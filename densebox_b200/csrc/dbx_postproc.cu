@@ -128,4 +128,51 @@ int decode_nms(const float* score, long s_img, long s_pix, const float* loc, lon
   return (int)cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------------ perspective warp
+// perspective_transform (DenseBox.py:3446-3481) = cv2.getPerspectiveTransform (host, 8 x 8 solve) + cv2.warpPerspective
+// (INTER_LINEAR, constant border 0).  The kernel restates OpenCV's fixed-point bilinear remap so that the result is
+// bit-identical: source coordinates in double ((M0 x + (M1 y + M2)) * 32 / w, round-half-even to 1/32 pixel), the four
+// weights as 15-bit integers ((32 - a)(32 - b) * 32 etc. — exact, they always sum to 32768), (sum + 2^14) >> 15.
+struct WarpMat { double m[9]; };  // INVERSE map: destination pixel -> source coordinates
+
+__global__ void __launch_bounds__(256) warp_perspective_u8_kernel(const unsigned char* __restrict__ src, int H, int W,
+                                                                  int C, WarpMat M, unsigned char* __restrict__ dst,
+                                                                  int dH, int dW) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= dW || y >= dH) return;
+  const double X0 = __dadd_rn(__dmul_rn(M.m[1], (double)y), M.m[2]);
+  const double Y0 = __dadd_rn(__dmul_rn(M.m[4], (double)y), M.m[5]);
+  const double W0 = __dadd_rn(__dmul_rn(M.m[7], (double)y), M.m[8]);
+  double w = __dadd_rn(W0, __dmul_rn(M.m[6], (double)x));
+  w = w != 0.0 ? __ddiv_rn(32.0, w) : 0.0;
+  double fX = __dmul_rn(__dadd_rn(X0, __dmul_rn(M.m[0], (double)x)), w);
+  double fY = __dmul_rn(__dadd_rn(Y0, __dmul_rn(M.m[3], (double)x)), w);
+  fX = fmax(-2147483648.0, fmin(2147483647.0, fX));
+  fY = fmax(-2147483648.0, fmin(2147483647.0, fY));
+  const int Xi = __double2int_rn(fX), Yi = __double2int_rn(fY);
+  const int sx = Xi >> 5, sy = Yi >> 5, a = Xi & 31, b = Yi & 31;
+  const int w00 = (32 - a) * (32 - b) * 32, w01 = a * (32 - b) * 32, w10 = (32 - a) * b * 32, w11 = a * b * 32;
+  const bool x0 = sx >= 0 && sx < W, x1 = sx + 1 >= 0 && sx + 1 < W, y0 = sy >= 0 && sy < H, y1 = sy + 1 >= 0 && sy + 1 < H;
+  unsigned char* o = dst + ((size_t)y * dW + x) * C;
+  for (int c = 0; c < C; ++c) {
+    int acc = 0;
+    if (y0 && x0) acc += w00 * (int)src[((size_t)sy * W + sx) * C + c];
+    if (y0 && x1) acc += w01 * (int)src[((size_t)sy * W + sx + 1) * C + c];
+    if (y1 && x0) acc += w10 * (int)src[((size_t)(sy + 1) * W + sx) * C + c];
+    if (y1 && x1) acc += w11 * (int)src[((size_t)(sy + 1) * W + sx + 1) * C + c];
+    const int v = (acc + (1 << 14)) >> 15;
+    o[c] = (unsigned char)(v < 0 ? 0 : (v > 255 ? 255 : v));
+  }
+}
+
+int warp_perspective_u8(const unsigned char* src, int H, int W, int C, const double* minv, unsigned char* dst, int dH,
+                        int dW, cudaStream_t st) {
+  if (!src || !dst || !minv || H <= 0 || W <= 0 || C <= 0 || C > 4 || dH <= 0 || dW <= 0) return DBX_ERR_ARG;
+  WarpMat M;
+  for (int i = 0; i < 9; ++i) M.m[i] = minv[i];
+  dim3 grid((dW + 255) / 256, dH);
+  warp_perspective_u8_kernel<<<grid, 256, 0, st>>>(src, H, W, C, M, dst, dH, dW);
+  return (int)cudaGetLastError();
+}
+
 }  // namespace dbx

@@ -47,3 +47,53 @@ def decode_nms(score_map, loc_map, lm_loc_map=None, K=10, nms_thresh=0.4, lm_hea
     dets, keep = dets.cpu().numpy().astype(np.float64), keep.cpu().numpy().astype(bool)
     ncol = 13 if lm_loc_map is not None else 5
     return [dets[i][keep[i]][:, :ncol] for i in range(N)]
+
+
+def perspective_matrix(src_pts):
+    """The homography of `perspective_transform` (DenseBox.py:3455-3476): the four landmark points (left-up, right-up,
+    right-down, left-down) are mapped onto the corners of their axis-aligned bounding rectangle.  Returns (M, Minv) as
+    float64 3 x 3 arrays — cv2.getPerspectiveTransform's 8 x 8 linear system and the cofactor inverse cv2 uses."""
+    src = np.asarray(src_pts, dtype=np.float32).astype(np.float64)
+    if src.shape != (4, 2):
+        raise ValueError("src_pts must be 4 points (x, y)")
+    lu, ru, rd, ld = src
+    min_x, max_x = min(lu[0], ld[0]), max(ru[0], rd[0])
+    min_y, max_y = min(lu[1], ru[1]), max(ld[1], rd[1])
+    dst = np.array([[min_x, min_y], [max_x, min_y], [max_x, max_y], [min_x, max_y]], dtype=np.float64)
+    A, b = np.zeros((8, 8)), np.zeros(8)
+    for i in range(4):
+        x, y = src[i]
+        X, Y = dst[i]
+        A[i] = [x, y, 1, 0, 0, 0, -x * X, -y * X]
+        A[i + 4] = [0, 0, 0, x, y, 1, -x * Y, -y * Y]
+        b[i], b[i + 4] = X, Y
+    M = np.append(np.linalg.solve(A, b), 1.0).reshape(3, 3)
+    a = M
+    det = (a[0, 0] * (a[1, 1] * a[2, 2] - a[1, 2] * a[2, 1]) - a[0, 1] * (a[1, 0] * a[2, 2] - a[1, 2] * a[2, 0])
+           + a[0, 2] * (a[1, 0] * a[2, 1] - a[1, 1] * a[2, 0]))
+    if det == 0.0:
+        raise ValueError("degenerate landmark quadrilateral")
+    d = 1.0 / det
+    Minv = np.array([
+        [(a[1, 1] * a[2, 2] - a[1, 2] * a[2, 1]) * d, (a[0, 2] * a[2, 1] - a[0, 1] * a[2, 2]) * d, (a[0, 1] * a[1, 2] - a[0, 2] * a[1, 1]) * d],
+        [(a[1, 2] * a[2, 0] - a[1, 0] * a[2, 2]) * d, (a[0, 0] * a[2, 2] - a[0, 2] * a[2, 0]) * d, (a[0, 2] * a[1, 0] - a[0, 0] * a[1, 2]) * d],
+        [(a[1, 0] * a[2, 1] - a[1, 1] * a[2, 0]) * d, (a[0, 1] * a[2, 0] - a[0, 0] * a[2, 1]) * d, (a[0, 0] * a[1, 1] - a[0, 1] * a[1, 0]) * d]])
+    return M, Minv
+
+
+def perspective_transform(img, src_pts):
+    """`perspective_transform(img, src_pts)` of the reference (DenseBox.py:3446-3481) on the GPU: rectify the plate
+    spanned by the four decoded landmarks into a canvas 1.5x the image.  img: uint8 [H,W,C] CUDA tensor (C <= 4);
+    returns a uint8 [int(1.5 H + .5), int(1.5 W + .5), C] CUDA tensor, bit-identical to cv2.warpPerspective."""
+    if not (torch.is_tensor(img) and img.is_cuda and img.dtype == torch.uint8 and img.dim() == 3):
+        raise RuntimeError("perspective_transform takes a uint8 [H,W,C] CUDA tensor (no CPU fallback)")
+    img = img.contiguous()
+    H, W, C = img.shape
+    _, minv = perspective_matrix(src_pts)
+    dH, dW = int(H * 1.5 + 0.5), int(W * 1.5 + 0.5)
+    out = torch.empty(dH, dW, C, dtype=torch.uint8, device=img.device)
+    m = (ctypes.c_double * 9)(*minv.reshape(-1).tolist())
+    with torch.cuda.device(img.device):
+        check(lib().dbx_warp_perspective_u8(ptr(img), c_int(H), c_int(W), c_int(C), m, ptr(out), c_int(dH), c_int(dW),
+                                            stream_ptr()), "warp_perspective_u8")
+    return out

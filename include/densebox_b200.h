@@ -74,6 +74,13 @@ int dbx_decode_nms_heat(const float* score, long s_img, long s_pix, const float*
                         const float* lmheat, long m_img, long m_pix, long m_ch, int N, int H4, int W4, int K,
                         double thresh, float* dets, int* keep, void* stream);
 
+/* perspective_transform (DenseBox.py:3446-3481): cv2.warpPerspective(INTER_LINEAR, constant border 0) of a uint8 HWC
+ * image, bit-identical to OpenCV's fixed-point remap.  minv: HOST pointer to the 3 x 3 INVERSE map (destination pixel
+ * -> source coordinates, row-major doubles; the Python wrapper derives it from the four landmark points as
+ * cv2.getPerspectiveTransform + inversion do). */
+int dbx_warp_perspective_u8(const unsigned char* src, int H, int W, int C, const double* minv, unsigned char* dst,
+                            int dH, int dW, void* stream);
+
 /* The fused loss on caller-provided head maps (same semantics as dbx_net_loss below; used by the drop-in
  * densebox_loss() op).  head: fp32 [B,60,60,HC] in the channel map below, rf: fp32 [B,60,60,RC] (variants 1,2).
  * scratch: >= 16 + 4*B bytes of device memory, zeroed once before the first call.  Outputs may be NULL.

@@ -12,6 +12,7 @@ The reference ships no tests or golden vectors, so the oracle is
   * decode_nms.npz — parse_out_MN / parse_DetLMLOC / parse_DetLM / NMS
   * ingest.npz     — file-name label parsers of DenseBoxDataset / LPPatchLM_Online / LPPatch_Online and the default
                      Resize + CenterCrop + ToTensor + Normalize transform on a random image
+  * perspective.npz — perspective_transform (cv2 homography + warpPerspective) on a random image
   * state_dict.npz — key -> shape of the three modules' state_dict() and the outcome of a strict load_state_dict round
                      trip between the reference modules and the drop-in modules (both directions)
 Loading shims: matplotlib stub, CUDA hidden during import, float64 labels for the loc-map
@@ -293,8 +294,28 @@ def gen_ingest(REF):
     np.savez_compressed(os.path.join(HERE, "ingest.npz"), **d)
 
 
+def gen_perspective(REF):
+    """perspective_transform (DenseBox.py:3446-3481) of the reference (cv2.getPerspectiveTransform + warpPerspective)
+    on a random RGB image for three landmark quadrilaterals, plus the homographies cv2 computes."""
+    import cv2
+    rs = np.random.RandomState(21)
+    img = rs.randint(0, 256, (96, 128, 3)).astype(np.uint8)
+    cases = [[[30, 20], [100, 26], [98, 60], [28, 52]], [[10.5, 8.25], [90, 5], [95.5, 70], [12, 66]],
+             [[40, 40], [80, 38], [84, 62], [37, 66]]]
+    outs = [REF.perspective_transform(img, c) for c in cases]
+    mats = []
+    for c in cases:
+        s = np.float32(c)
+        lu, ru, rd, ld = s
+        mnx, mxx, mny, mxy = min(lu[0], ld[0]), max(ru[0], rd[0]), min(lu[1], ru[1]), max(ld[1], rd[1])
+        mats.append(cv2.getPerspectiveTransform(s, np.float32([[mnx, mny], [mxx, mny], [mxx, mxy], [mnx, mxy]])))
+    np.savez_compressed(os.path.join(HERE, "perspective.npz"), img=img, pts=np.array(cases, np.float64), out0=outs[0],
+                        out1=outs[1], out2=outs[2], mats=np.array(mats))
+
+
 if __name__ == "__main__":
     REF = load_reference()
+    gen_perspective(REF)
     gen_ingest(REF)
     gen_state_dict(REF)
     gen_geometry(REF)

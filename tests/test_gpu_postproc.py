@@ -61,3 +61,24 @@ def test_decode_on_engine_outputs_strided():
     for i in range(2):
         ref = O.decode(score[i:i + 1].cpu().contiguous(), loc[i:i + 1].cpu().contiguous(), None, K=7)
         assert np.array_equal(got[i], ref[sorted(O.nms(ref, 0.4))])
+
+
+def test_perspective_transform_matches_reference_fixture():
+    """perspective_transform (DenseBox.py:3446-3481) on the GPU against the image the reference produced with
+    cv2.warpPerspective: OpenCV's fixed-point bilinear remap restated bit for bit.  The homography comes from a
+    different LU solve than cv2's (1e-15 relative), so a source coordinate may land on the other side of a 1/32-pixel
+    rounding boundary for a handful of pixels: at most 0.05 % of the values may differ, and then by what a 1/32-pixel
+    shift does on a white-noise image (<= 8 grey levels); two of the three cases match bit for bit."""
+    from densebox_b200 import perspective_transform
+    d = np.load(os.path.join(G, "perspective.npz"))
+    img = torch.from_numpy(d["img"]).cuda()
+    exact = 0
+    for i, pts in enumerate(d["pts"]):
+        got = perspective_transform(img, pts).cpu().numpy()
+        want = d["out%d" % i]
+        assert got.shape == want.shape
+        diff = np.abs(got.astype(np.int32) - want.astype(np.int32))
+        assert diff.max() <= 8 and (diff > 0).mean() <= 5e-4, (i, diff.max(), (diff > 0).mean())
+        exact += int(diff.max() == 0)
+        assert want.max() > 0
+    assert exact >= 2

@@ -166,3 +166,14 @@ def test_label_parser_and_ingest_table_match_reference_datasets():
     via_table = torch.stack([tab[c][u8[..., c].long()] for c in range(3)])
     assert torch.equal(via_table, torch.from_numpy(d["img_norm"]))
     assert torch.equal(data.normalize_u8(u8[None])[0], torch.from_numpy(d["img_norm"]))
+
+
+def test_perspective_matrix_matches_cv2():
+    """f-4: the homography of perspective_transform (DenseBox.py:3455-3476) against cv2.getPerspectiveTransform
+    (fixture): 1e-12 relative (two LU solves of the same 8 x 8 system)."""
+    from densebox_b200.postproc import perspective_matrix
+    d = np.load(os.path.join(G, "perspective.npz"))
+    for pts, want in zip(d["pts"], d["mats"]):
+        M, Minv = perspective_matrix(pts)
+        assert np.abs(M - want).max() <= 1e-12 * np.abs(want).max()
+        assert np.abs(M @ Minv - np.eye(3)).max() <= 1e-9
