@@ -859,11 +859,185 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
   }
 }
 
+// ------------------------------------------------------------------------------------------------ wgrad, 64 -> 64
+// conv1_2 (3x3 pad 1, Cin = Cout = 64): with output channels as M the 128-row MMA is half empty (round-1/2 profile:
+// 849 TFLOP/s, 0.160 ms, 4 % of the step).  Here the roles are swapped: M = (tap, input channel) — the nine taps of
+// the three column-shifted 8 x 18 input boxes are 4.5 tiles of 128 rows (two 64-channel atoms per tile: a row shift is
+// one 1024-byte atom inside a box, the next column is the next box) — and N = Cout = 64, K = the 128 pixels of a box.
+// All nine taps of a pixel box are accumulated from ONE load of (dY box + 3 input boxes): 5 MMAs of 128 x 64 per K
+// step instead of 3 x (128 x 192 with half the rows wasted), 70 KB of operands per box instead of 102 KB.  Each CTA owns
+// a contiguous range of pixel boxes and keeps ALL 9 x 64 x 64 partial sums in TMEM (5 x 64 columns) for its whole life:
+// one epilogue per CTA (fp32 red.add into dw[co][tap * 64 + ci]).
+struct Wgrad64Params {
+  int tiles_w, tiles_h, boxes_total, boxes_per_cta;
+  FastDiv fd_tw, fd_twh;
+  float* dw;
+  uint32_t idesc;
+};
+static constexpr uint32_t kW64Box = 18432u, kW64Dy = 16384u, kW64Stage = 3u * kW64Box + kW64Dy;  // 71 680 B
+static constexpr int kW64Stages = 3;
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_wgrad64_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ CUtensorMap tmX,
+                    const Wgrad64Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t full_bar[kW64Stages], empty_bar[kW64Stages], tfull_bar;
+  __shared__ uint32_t tmem_base_s;
+  griddep_launch_dependents();
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmDy);
+    tma_prefetch_desc(&tmX);
+    for (int s = 0; s < kW64Stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(&tfull_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc(&tmem_base_s, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  griddep_wait();
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
+  const int b_begin = (int)blockIdx.x * p.boxes_per_cta;
+  int b_end = b_begin + p.boxes_per_cta; if (b_end > p.boxes_total) b_end = p.boxes_total;
+
+  if (warp == 0) {
+    int stage = 0; uint32_t phase = 0;
+    for (int b = b_begin; b < b_end; ++b) {
+      const int nq = p.fd_twh.div(b), brem = b - nq * (p.tiles_w * p.tiles_h), hq = p.fd_tw.div(brem);
+      const int w0 = (brem - hq * p.tiles_w) * 8, h0 = hq * 16;
+      mbar_wait_a(empty0 + 8u * stage, phase ^ 1);
+      if (elect_one_sync()) {
+        const uint32_t sa = smem_base + (uint32_t)stage * kW64Stage, fb = full0 + 8u * stage;
+        mbar_arrive_expect_tx_a(fb, kW64Stage);
+#pragma unroll
+        for (int s = 0; s < 3; ++s) tma_load_4d_a(&tmX, fb, sa + (uint32_t)s * kW64Box, 0, w0 + s - 1, h0 - 1, nq);
+        tma_load_4d_a(&tmDy, fb, sa + 3u * kW64Box, 0, w0, h0, nq);
+      }
+      __syncwarp();
+      if (++stage == kW64Stages) { stage = 0; phase ^= 1; }
+    }
+  } else if (warp == 1) {
+    int stage = 0; uint32_t phase = 0;
+    // A tiles (MN-major SW128: two 64-channel atoms LBO apart, 8-pixel groups SBO = 1024 B apart): byte offset of the
+    // first atom inside the stage and the distance to the second — tile j holds taps (r, s):
+    //   0: (0,0),(1,0)   1: (2,0),(0,1)   2: (1,1),(2,1)   3: (0,2),(1,2)   4: (2,2), -
+    const uint32_t a_off[5] = {0u, 2048u, kW64Box + 1024u, 2u * kW64Box, 2u * kW64Box + 2048u};
+    const uint32_t a_lbo[5] = {1024u, kW64Box - 2048u, 1024u, 1024u, 1024u};
+    uint64_t a_hi[5];
+#pragma unroll
+    for (int j = 0; j < 5; ++j) a_hi[j] = umma_smem_desc_sw128(0, a_lbo[j], 1024);
+    const uint64_t b_hi = umma_smem_desc_sw128(0, 1024, 1024);
+    for (int b = b_begin; b < b_end; ++b) {
+      mbar_wait_a(full0 + 8u * stage, phase);
+      tc_fence_after();
+      if (elect_one_sync()) {
+        const uint32_t s_lo = (smem_base + (uint32_t)stage * kW64Stage) >> 4;
+        const uint64_t db = b_hi | (uint64_t)(s_lo + ((3u * kW64Box) >> 4));
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {       // 16 pixel rows = 2048 B = 128 x 16 B per K step
+#pragma unroll
+          for (int j = 0; j < 5; ++j)
+            umma_bf16(tmem + (uint32_t)(64 * j), (a_hi[j] | (uint64_t)(s_lo + (a_off[j] >> 4))) + 128u * ks, db + 128u * ks,
+                      p.idesc, (uint32_t)((b > b_begin) | (ks != 0)));
+        }
+        umma_commit_a(empty0 + 8u * stage);
+      }
+      __syncwarp();
+      if (++stage == kW64Stages) { stage = 0; phase ^= 1; }
+    }
+    if (elect_one_sync()) umma_commit_a(smem_u32(&tfull_bar));
+    __syncwarp();
+  } else if (b_begin < b_end) {
+    // epilogue: TMEM lane = (tap half, input channel), column = output channel.  dw[co][tap * 64 + ci] wants
+    // consecutive ci per store, a thread holds consecutive co: transpose each 128 x 64 tile through shared memory (the
+    // operand stages are free once the last MMA has committed) and add with 16-byte vector reds — a quarter of the
+    // atomic operations of the scalar form, which all 148 CTAs issue at the same moment.
+    // Measured: 0.160 -> 0.130 ms.  Not more, because with N = 64 every MMA re-reads its 4 KB A tile and the 2 KB B tile
+    // from shared memory: 6 KB per 32 tensor cycles = 192 B/clk against the 128 B/clk an SM's shared memory delivers
+    // (43 FLOP per shared-memory byte where 64 are needed): the 64-channel layers are shared-memory-bound by shape.
+    const int q = warp & 3, et = (int)threadIdx.x - 64;   // 128 epilogue threads
+    const int row = q * 32 + lane;
+    const int taps[5][2] = {{0, 3}, {6, 1}, {4, 7}, {2, 5}, {8, -1}};
+    float* T = reinterpret_cast<float*>(smem);            // [64 co][128 rows] fp32 = 32 KB
+    mbar_wait(&tfull_bar, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int j = 0; j < 5; ++j) {
+      const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(64 * j);
+#pragma unroll
+      for (int c0 = 0; c0 < 64; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_x32(taddr + c0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) T[(c0 + i) * 128 + row] = __uint_as_float(v[i]);
+      }
+      named_bar_sync(2, 128);
+      // thread: rows 4 (et & 31) .. + 3 (same tap half), output channels (et >> 5) + 4 k
+      const int r4 = (et & 31) * 4, half = r4 >> 6, tap = taps[j][half];
+      if (tap >= 0) {
+        float* dst = p.dw + tap * 64 + (r4 & 63);
+#pragma unroll 4
+        for (int k = 0; k < 16; ++k) {
+          const int co = (et >> 5) + 4 * k;
+          const float4 f = *reinterpret_cast<const float4*>(T + co * 128 + r4);
+          red_add_v4(dst + (size_t)co * 576, f.x, f.y, f.z, f.w);
+        }
+      }
+      named_bar_sync(2, 128);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+}
+
+static int conv_wgrad64(const Act& x, const Act& dy, float* dw, cudaStream_t stream) {
+  Tile t{};
+  t.tw = 8; t.th = 16; t.tn = 1;
+  t.tiles_w = (dy.W + 7) / 8; t.tiles_h = (dy.H + 15) / 16; t.tiles_n = dy.N;
+  Tile tx = t; tx.th = 18;
+  CUtensorMap tmDy, tmX;
+  int rc = encode_act_map(&tmDy, dy, t);
+  if (rc) return rc;
+  rc = encode_act_map(&tmX, x, tx);
+  if (rc) return rc;
+  Wgrad64Params p{};
+  p.tiles_w = t.tiles_w; p.tiles_h = t.tiles_h; p.boxes_total = t.count();
+  const int ctas = p.boxes_total < tensor_sms() ? p.boxes_total : tensor_sms();
+  p.boxes_per_cta = (p.boxes_total + ctas - 1) / ctas;
+  p.fd_tw = FastDiv::make(p.tiles_w); p.fd_twh = FastDiv::make(p.tiles_w * p.tiles_h);
+  p.dw = dw;
+  p.idesc = umma_idesc_bf16(128, 64, 1, 1);
+  static SmemAttrOnce attr_once;
+  const int smem = kW64Stages * (int)kW64Stage + 2048;   // + alignment slack + the over-read of the last half tile
+  { const int arc = set_max_smem_once((const void*)conv_wgrad64_kernel, smem, &attr_once); if (arc) return arc; }
+  cudaLaunchConfig_t cfg{};
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cfg.gridDim = dim3((p.boxes_total + p.boxes_per_cta - 1) / p.boxes_per_cta);
+  return (int)cudaLaunchKernelEx(&cfg, conv_wgrad64_kernel, tmDy, tmX, p);
+}
+
 int conv_wgrad(const Act& x, const Act& dy, int R, int S, int pad, float* dw, int block_n, cudaStream_t stream) {
   const int block_n_in = block_n;
   if (!x.ptr || !dy.ptr || !dw) return DBX_ERR_ARG;
   if (x.C % 64 || dy.C % 16) return DBX_ERR_ARG;
   if (dy.H != x.H + 2 * pad - R + 1 || dy.W != x.W + 2 * pad - S + 1 || dy.N != x.N) return DBX_ERR_ARG;
+  if (R == 3 && S == 3 && pad == 1 && x.C == 64 && dy.C == 64 && block_n <= 0) {  // conv1_2: roles swapped, see above
+    const char* e = ab_env("DBX_WGRAD64");
+    if (!(e && e[0] == '0')) return conv_wgrad64(x, dy, dw, stream);
+  }
   const int q_total = R * S * (x.C / 64);
   if (block_n <= 0) {
     block_n = 256;
