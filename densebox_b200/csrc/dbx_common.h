@@ -67,6 +67,14 @@ struct ConvEpilogue {
   int out_fp32 = 0;            // output element type: 0 bf16, 1 fp32
   int force_cta2 = -1;         // -1 = auto, 0 = never pair CTAs (tcgen05.mma.cta_group::2)
   int epi_bufs = 0;            // 0 = auto; 2/4/8 epilogue staging boxes (short-K GEMMs with a mask want a deep ring)
+  // 2x2 max-pool fused behind bias + ReLU (conv1_2 -> pool1, conv2_2 -> pool2, DenseBox.py:186-191): the epilogue
+  // writes the POOLED activation (view pool_out: buffer, channel stride, channel offset) and, when pool_idx is given,
+  // the 2-bit arg-max map of maxpool2x2_fwd; the full-resolution output is not stored at all (nothing downstream
+  // reads it: the backward pass works from the pooled map + the arg-max map).  Falls back to conv + maxpool2x2_fwd
+  // (which does store `out`) when the launch cannot use 8 x 16 column-box tiles.
+  void* pool_out = nullptr;
+  int pool_cs = 0, pool_coff = 0;
+  void* pool_idx = nullptr;
   float* colsum = nullptr;     // fp32 [cout] or null: colsum[c] += sum over pixels of out[.., c] (as stored, bf16-rounded).
                                // A data-gradient launch uses it to produce the bias gradient of the layer below
                                // in its own epilogue instead of re-reading dY from HBM; requires bias == nullptr.

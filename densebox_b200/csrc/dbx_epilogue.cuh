@@ -35,6 +35,9 @@ struct EpiArgs {
   const unsigned long long* rng; int rng_channels;
   float* csum = nullptr;                // smem fp32 [8][cout] (one copy per row group): running column sums of
                                         // everything this CTA stored, or null
+  bf16* pool_out = nullptr;             // fused 2x2 max-pool: pooled NHWC view (see ConvEpilogue::pool_out); 8 x 16 tiles
+  int pool_cs = 0, pool_coff = 0;
+  unsigned short* pool_idx = nullptr;   // 2-bit arg-max map (u16 per pooled pixel and 8 channels) or null
 };
 
 __device__ __forceinline__ uint32_t bf162_as_u32(__nv_bfloat162 h) { return *reinterpret_cast<uint32_t*>(&h); }
@@ -56,6 +59,41 @@ __device__ __forceinline__ void epi_relu16(uint32_t* pk) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) pk[i] = bf162_as_u32(__hmax2(u32_as_bf162(pk[i]), z));
 }
+__device__ __forceinline__ uint32_t sel32(uint32_t g, uint32_t a, uint32_t b) { return (a & g) | (b & ~g); }  // g ? a : b, bitwise
+
+// 2x2 max-pool of a warp's 4 x 8 pixel patch (lane = 8 * row + column) over the 32 channels each lane holds as 16
+// packed bf16x2 words.  The four lanes of a window (lane ^ 1: next column, lane ^ 8: next row) split the channels:
+// after a two-step butterfly the lane at window position (dx, dy) owns words 8 dx + 4 dy .. + 3 of the pooled pixel.
+// First maximum in scan order wins ties (torch max_pool2d), arg = 2 dy + dx as in maxpool2x2_fwd_kernel.
+// Returns the 8 x 2 arg bits of the lane's eight channels.
+__device__ __forceinline__ uint32_t epi_pool2x2(const uint32_t* pk, int lane, uint32_t* m) {
+  const bool dx = lane & 1, dy = (lane >> 3) & 1;
+  const __nv_bfloat162* dummy = nullptr; (void)dummy;
+  uint32_t r[8], a1[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const uint32_t own = dx ? pk[8 + k] : pk[k], snd = dx ? pk[k] : pk[8 + k];
+    const uint32_t rcv = __shfl_xor_sync(0xffffffffu, snd, 1);
+    const uint32_t a = dx ? rcv : own, b = dx ? own : rcv;          // the column-0 / column-1 value of the window
+    const uint32_t g = __hgt2_mask(u32_as_bf162(b), u32_as_bf162(a));
+    r[k] = sel32(g, b, a);
+    a1[k] = g;
+  }
+  uint32_t bits = 0u;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const uint32_t own = dy ? r[4 + k] : r[k], snd = dy ? r[k] : r[4 + k];
+    const uint32_t oa = dy ? a1[4 + k] : a1[k], sa = dy ? a1[k] : a1[4 + k];
+    const uint32_t rcv = __shfl_xor_sync(0xffffffffu, snd, 8), ra = __shfl_xor_sync(0xffffffffu, sa, 8);
+    const uint32_t top = dy ? rcv : own, bot = dy ? own : rcv, ta = dy ? ra : oa, ba = dy ? oa : ra;
+    const uint32_t g = __hgt2_mask(u32_as_bf162(bot), u32_as_bf162(top));
+    m[k] = sel32(g, bot, top);
+    const uint32_t arg = (sel32(g, ba, ta) & 0x00010001u) | ((g & 0x00010001u) << 1);   // 2 bits per 16-bit half
+    bits |= ((arg & 3u) << (4 * k)) | (((arg >> 16) & 3u) << (4 * k + 2));
+  }
+  return bits;
+}
+
 __device__ __forceinline__ void epi_dropout16(uint32_t* pk, uint32_t bits) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
@@ -182,9 +220,23 @@ __device__ __forceinline__ void epilogue_tma(const EpiArgs& e, const CUtensorMap
               }
             }
           }
+          if (e.pool_out) {
+            // fused 2x2 max-pool: no staging box, no TMA store — the pooled quarter of each window goes straight out
+            uint32_t m[4];
+            const uint32_t bits = epi_pool2x2(pk, lane, m);
+            const int px = w0 + r_w, py = h0 + r_h;
+            if (px < e.out_W && py < e.out_H) {
+              const int wb = ((lane & 1) ? 8 : 0) + (((lane >> 3) & 1) ? 4 : 0);
+              const size_t pp = ((size_t)(n0 + r_n) * (e.out_H >> 1) + (py >> 1)) * (e.out_W >> 1) + (px >> 1);
+              const int c = ch + 2 * wb;
+              *reinterpret_cast<uint4*>(e.pool_out + pp * e.pool_cs + e.pool_coff + c) = make_uint4(m[0], m[1], m[2], m[3]);
+              if (e.pool_idx) e.pool_idx[pp * (e.cout >> 3) + (c >> 3)] = (unsigned short)bits;
+            }
+          } else {
 #pragma unroll
           for (int g = 0; g < 4; ++g)
             *reinterpret_cast<uint4*>(sb + chunk[g]) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+          }
         }
       } else {
         // ---- ragged tail (block_n not a multiple of 64): 16 columns at a time, scalar guards
@@ -231,6 +283,7 @@ __device__ __forceinline__ void epilogue_tma(const EpiArgs& e, const CUtensorMap
           }
         }
       }
+      if (e.pool_out) continue;  // nothing staged, nothing to store (launcher guarantees whole 64-column blocks)
       fence_proxy_async_smem();
       if (leader) {
         // Before the barrier of sub-block q the leader proves free the box that is written next: the box of

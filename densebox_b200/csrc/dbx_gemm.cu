@@ -174,6 +174,7 @@ struct FpropParams {
   const unsigned long long* rng; int rng_channels;  // aux_mode 3: in-place Philox dropout
   int cta2;                // 1: CTA pairs drive tcgen05.mma.cta_group::2 (launched with cluster size 2)
   int tma_epi, nbuf, nbuf_log2, nsb;  // bf16 outputs: epilogue staged through `nbuf` (2/4/8) smem boxes, `nsb` 64-column blocks/tile
+  bf16* pool_out; int pool_cs, pool_coff; unsigned short* pool_idx;  // fused 2x2 max-pool (ConvEpilogue::pool_out)
 };
 
 // kMode: 1 / 2 / 4 = K blocks (one tap x 64 channels) per pipeline stage; 3 = column-box mode for 3x3 pad-1 layers:
@@ -397,6 +398,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       ea.tw = p.tw; ea.th = p.th; ea.box_rows = p.tw * p.th * p.tn;
       ea.out_W = p.out_W; ea.out_H = p.out_H; ea.rng = p.rng; ea.rng_channels = p.rng_channels;
       ea.csum = csum;
+      ea.pool_out = p.pool_out; ea.pool_cs = p.pool_cs; ea.pool_coff = p.pool_coff; ea.pool_idx = p.pool_idx;
       const int my_tiles = u0 < total ? (total - 1 - u0) / ustep + 1 : 0;
       auto tile_of = [&](int it, int& nt, int& w0, int& h0, int& n0) {
         DBX_UNIT_TILE(u0 + it * ustep, nt_, mt_);
@@ -634,6 +636,19 @@ int conv_fprop(const Act& x, const void* wk, int R, int S, int pad, const Act& o
   p.aux = (const bf16*)epi.aux; p.aux_cs = epi.aux_cs; p.aux_coff = epi.aux_coff; p.aux_mode = epi.aux_mode;
   p.out = out.ptr; p.out_cs = out.cs; p.out_coff = out.coff; p.out_fp32 = epi.out_fp32;
   p.rng = epi.rng; p.rng_channels = epi.rng_channels;
+  // fused 2x2 max-pool: needs the 8 x 16 column-box tiles (a warp of the epilogue = a 4 x 8 pixel patch), whole
+  // 64-column blocks, even map sizes, no mask and no fused column sums
+  bool pool_after = false;
+  if (epi.pool_out) {
+    const bool ok = colbox && tma_epi && epi.aux_mode == 0 && !epi.colsum && block_n % 64 == 0 && out.C % 64 == 0 &&
+                    out.H % 2 == 0 && out.W % 2 == 0 && epi.pool_cs % 8 == 0 && epi.pool_coff % 8 == 0;
+    if (ok) {
+      p.pool_out = (bf16*)epi.pool_out; p.pool_cs = epi.pool_cs; p.pool_coff = epi.pool_coff;
+      p.pool_idx = (unsigned short*)epi.pool_idx;
+    } else {
+      pool_after = true;  // same result from the stand-alone kernel behind this launch (which then stores `out`)
+    }
+  }
 
   if (p.kps == 3) p.kps = 2;
   typedef void (*FpropFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const FpropParams);
@@ -667,6 +682,11 @@ int conv_fprop(const Act& x, const void* wk, int R, int S, int pad, const Act& o
   cfg.gridDim = dim3(grid);
   rc = (int)cudaLaunchKernelEx(&cfg, fn, tmA, tmB, tmO, tmX, p);
   if (rc == 0 && colsum_after) rc = colsum(out, epi.colsum, stream);
+  if (rc == 0 && pool_after) {
+    Act po = out;
+    po.ptr = epi.pool_out; po.H = out.H / 2; po.W = out.W / 2; po.cs = epi.pool_cs; po.coff = epi.pool_coff;
+    rc = maxpool2x2_fwd(out, po, stream, epi.pool_idx);
+  }
   return rc;
 }
 

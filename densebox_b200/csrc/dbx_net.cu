@@ -364,6 +364,16 @@ struct Net {
           conv_fprop(x, wk_of(grp), R, R, pad, out, e, block_n, st));
     return DBX_OK;
   }
+  // conv + bias + ReLU + 2x2 max-pool in one launch (ConvEpilogue::pool_out): `pooled` and the arg-max map are
+  // written, the full-resolution activation `full` only when the launch has to fall back to the stand-alone pool.
+  int conv_pool(const Act& x, const char* grp, const Act& full, const Act& pooled, void* idx, cudaStream_t st) {
+    ConvEpilogue e;
+    e.bias = bias_of(grp); e.relu = 1;
+    e.pool_out = pooled.ptr; e.pool_cs = pooled.cs; e.pool_coff = pooled.coff; e.pool_idx = idx;
+    DBX_K((std::string("fprop:") + grp).c_str(), 2.0 * pixels(full) * macs_of(grp),
+          conv_fprop(x, wk_of(grp), 3, 3, 1, full, e, 0, st));
+    return DBX_OK;
+  }
   // bias_below: the group whose bias gradient is the column sum of dx (dx = dZ of that layer): produced by this
   // launch's epilogue (ConvEpilogue::colsum) instead of a separate pass over dx; the matching wgrad() call then
   // passes bias_done = true.
@@ -443,11 +453,24 @@ struct Net {
     } else {
       DBX_TRY(conv(col0, "conv1_1", 1, 0, a11, true, nullptr, 0, 0, false, 0, st));
     }
-    DBX_TRY(conv(a11, "conv1_2", 3, 1, a12, true, nullptr, 0, 0, false, 0, st));
-    DBX_K("pool_fwd", 0.0, maxpool2x2_fwd(a12, p1, st, train ? buf("pi1") : nullptr));
+    // pool1 / pool2 ride in the epilogues of conv1_2 / conv2_2: a12 / a22 never reach HBM (nothing else reads them:
+    // the backward pass works from the pooled maps + arg-max maps).  DBX_POOL_FUSE=0 / DBX_POOL_IDX=0: separate kernels.
+    bool pool_fuse = true;
+    { const char* e1 = ab_env("DBX_POOL_FUSE"); const char* e2 = ab_env("DBX_POOL_IDX");
+      if ((e1 && e1[0] == '0') || (e2 && e2[0] == '0')) pool_fuse = false; }
+    if (pool_fuse) {
+      DBX_TRY(conv_pool(a11, "conv1_2", a12, p1, train ? buf("pi1") : nullptr, st));
+    } else {
+      DBX_TRY(conv(a11, "conv1_2", 3, 1, a12, true, nullptr, 0, 0, false, 0, st));
+      DBX_K("pool_fwd", 0.0, maxpool2x2_fwd(a12, p1, st, train ? buf("pi1") : nullptr));
+    }
     DBX_TRY(conv(p1, "conv2_1", 3, 1, a21, true, nullptr, 0, 0, false, 0, st));
-    DBX_TRY(conv(a21, "conv2_2", 3, 1, a22, true, nullptr, 0, 0, false, 0, st));
-    DBX_K("pool_fwd", 0.0, maxpool2x2_fwd(a22, p2, st, train ? buf("pi2") : nullptr));
+    if (pool_fuse) {
+      DBX_TRY(conv_pool(a21, "conv2_2", a22, p2, train ? buf("pi2") : nullptr, st));
+    } else {
+      DBX_TRY(conv(a21, "conv2_2", 3, 1, a22, true, nullptr, 0, 0, false, 0, st));
+      DBX_K("pool_fwd", 0.0, maxpool2x2_fwd(a22, p2, st, train ? buf("pi2") : nullptr));
+    }
     DBX_TRY(conv(p2, "conv3_1", 3, 1, a31, true, nullptr, 0, 0, false, 0, st));
     DBX_TRY(conv(a31, "conv3_2", 3, 1, a32, true, nullptr, 0, 0, false, 0, st));
     DBX_TRY(conv(a32, "conv3_4", 3, 1, a34, true, nullptr, 0, 0, false, 0, st));  // conv3_3 skipped (:193-195)

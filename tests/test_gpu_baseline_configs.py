@@ -160,14 +160,31 @@ def test_inference_1024_decode_nms():
             assert abs(row[4] - flat[p].item()) <= tol["rf"]
 
 
+def unpool(p, idx):
+    """The full-resolution activation as far as anything downstream can tell, from the pooled map p [N,h,w,C] and the
+    2-bit arg-max map idx [N,h,w,C/8] (u16, 2 bits per channel: 2 dy + dx): the pooled value at the arg-max position,
+    zero elsewhere.  conv1_2 / conv2_2 no longer store their full-resolution outputs (the 2x2 max-pool rides in their
+    epilogue); max-pooling this tensor picks the same positions and its ReLU mask equals the engine's wherever a
+    gradient can flow (only the arg-max of a window receives one, and it is masked by p > 0)."""
+    N, h, w, C = p.shape
+    bits = (idx.to(torch.int32) & 0xFFFF).reshape(N, h, w, C // 8, 1)
+    arg = ((bits >> (2 * torch.arange(8, device=p.device, dtype=torch.int32))) & 3).reshape(N, h, w, 1, C).long()
+    full = torch.zeros(N, h, w, 4, C, dtype=p.dtype, device=p.device)
+    full.scatter_(3, arg, p.unsqueeze(3))
+    return full.view(N, h, w, 2, 2, C).permute(0, 1, 3, 2, 4, 5).reshape(N, 2 * h, 2 * w, C)
+
+
 def engine_acts(eng, variant):
     """NCHW fp32 copies of the engine's stored activations under the names oracle.forward(frozen=...) expects."""
     N, H, W = eng.N, eng.H, eng.W
     bf = torch.bfloat16
     nchw = lambda t: t.float().permute(0, 3, 1, 2).contiguous().cpu()
     a = {}
-    for name, buf, h, w, c in (("conv1_1", "a11", H, W, 64), ("conv1_2", "a12", H, W, 64),
-                               ("conv2_1", "a21", H // 2, W // 2, 128), ("conv2_2", "a22", H // 2, W // 2, 128),
+    a["conv1_2"] = nchw(unpool(eng.buffer("p1", bf, (N, H // 2, W // 2, 64)),
+                               eng.buffer("pi1", torch.int16, (N, H // 2, W // 2, 8))))
+    a["conv2_2"] = nchw(unpool(eng.buffer("p2", bf, (N, H // 4, W // 4, 128)),
+                               eng.buffer("pi2", torch.int16, (N, H // 4, W // 4, 16))))
+    for name, buf, h, w, c in (("conv1_1", "a11", H, W, 64), ("conv2_1", "a21", H // 2, W // 2, 128),
                                ("conv3_1", "a31", H // 4, W // 4, 256), ("conv3_2", "a32", H // 4, W // 4, 256),
                                ("conv4_1", "a41", H // 8, W // 8, 512), ("conv4_2", "a42", H // 8, W // 8, 512),
                                ("conv4_3", "a43", H // 8, W // 8, 512), ("conv4_4", "a44", H // 8, W // 8, 512)):

@@ -126,3 +126,41 @@ def test_conv1_1_pairs_layout_matches_64_channel_layout():
             assert scale > 0 and err <= 1e-4, (n, err)
         else:
             assert err <= 2e-5, (n, err)                          # red.add order in wgrad only
+
+
+def _fwd_bwd(fuse_pool):
+    from densebox_b200 import densebox_loss
+    os.environ["DBX_POOL_FUSE"] = "1" if fuse_pool else "0"
+    try:
+        _, net = build("lm")
+        net = net.cuda().eval()
+        x, lab, rand, lm_rand = make_inputs(3, "lm")
+        outs = net(x.cuda())
+        eng = next(iter(net._engines.values()))
+        N = 3
+        pooled = [eng.buffer("p1", torch.bfloat16, (N, 120, 120, 64)).clone(), eng.buffer("p2", torch.bfloat16, (N, 60, 60, 128)).clone(),
+                  eng.buffer("pi1", torch.int16).clone(), eng.buffer("pi2", torch.int16).clone()]
+        score, loc, lm, rf = outs
+        L = densebox_loss(score, loc, lab["bbox"], rand_neg_idx=rand, lm=lm, rf=rf, vertices=lab["vertices"],
+                          lm_rand_neg_idx=lm_rand)
+        L.backward()
+        torch.cuda.synchronize()
+        g = {n: p.grad.detach().float().cpu() for n, p in net.named_parameters() if p.grad is not None}
+        return [o.detach().cpu() for o in outs], pooled, g, float(L.detach())
+    finally:
+        os.environ.pop("DBX_POOL_FUSE", None)
+
+
+def test_pool_fused_into_conv_epilogue_matches_separate_pool_kernel():
+    """pool1 / pool2 computed inside the epilogues of conv1_2 / conv2_2 (the full-resolution activations never reach
+    HBM) against conv + maxpool2x2_fwd_kernel: pooled maps, arg-max maps (first maximum wins ties), head outputs and
+    loss bit-identical; gradients equal up to the summation order of the atomics."""
+    outs_a, pooled_a, g_a, L_a = _fwd_bwd(False)
+    outs_b, pooled_b, g_b, L_b = _fwd_bwd(True)
+    for a, b in zip(pooled_a, pooled_b):
+        assert torch.equal(a, b)
+    for a, b in zip(outs_a, outs_b):
+        assert torch.equal(a, b)
+    assert L_a == L_b
+    for n in g_a:
+        assert (g_a[n] - g_b[n]).abs().max().item() <= 1e-4 * g_a[n].abs().max().item() + 1e-30, n
