@@ -75,6 +75,7 @@ struct ConvEpilogue {
   void* pool_out = nullptr;
   int pool_cs = 0, pool_coff = 0;
   void* pool_idx = nullptr;
+  int pool_keep_full = 0;      // 1: store the full-resolution output too (conv3_4: the fusion buffer needs it)
   float* colsum = nullptr;     // fp32 [cout] or null: colsum[c] += sum over pixels of out[.., c] (as stored, bf16-rounded).
                                // A data-gradient launch uses it to produce the bias gradient of the layer below
                                // in its own epilogue instead of re-reading dY from HBM; requires bias == nullptr.

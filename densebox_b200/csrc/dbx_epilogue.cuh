@@ -38,6 +38,7 @@ struct EpiArgs {
   bf16* pool_out = nullptr;             // fused 2x2 max-pool: pooled NHWC view (see ConvEpilogue::pool_out); 8 x 16 tiles
   int pool_cs = 0, pool_coff = 0;
   unsigned short* pool_idx = nullptr;   // 2-bit arg-max map (u16 per pooled pixel and 8 channels) or null
+  int pool_keep_full = 0;               // also stage + TMA-store the full-resolution tile
 };
 
 __device__ __forceinline__ uint32_t bf162_as_u32(__nv_bfloat162 h) { return *reinterpret_cast<uint32_t*>(&h); }
@@ -232,7 +233,8 @@ __device__ __forceinline__ void epilogue_tma(const EpiArgs& e, const CUtensorMap
               *reinterpret_cast<uint4*>(e.pool_out + pp * e.pool_cs + e.pool_coff + c) = make_uint4(m[0], m[1], m[2], m[3]);
               if (e.pool_idx) e.pool_idx[pp * (e.cout >> 3) + (c >> 3)] = (unsigned short)bits;
             }
-          } else {
+          }
+          if (!e.pool_out || e.pool_keep_full) {
 #pragma unroll
           for (int g = 0; g < 4; ++g)
             *reinterpret_cast<uint4*>(sb + chunk[g]) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
@@ -283,7 +285,7 @@ __device__ __forceinline__ void epilogue_tma(const EpiArgs& e, const CUtensorMap
           }
         }
       }
-      if (e.pool_out) continue;  // nothing staged, nothing to store (launcher guarantees whole 64-column blocks)
+      if (e.pool_out && !e.pool_keep_full) continue;  // nothing staged, nothing to store (whole 64-column blocks only)
       fence_proxy_async_smem();
       if (leader) {
         // Before the barrier of sub-block q the leader proves free the box that is written next: the box of

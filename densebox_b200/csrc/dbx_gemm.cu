@@ -174,7 +174,7 @@ struct FpropParams {
   const unsigned long long* rng; int rng_channels;  // aux_mode 3: in-place Philox dropout
   int cta2;                // 1: CTA pairs drive tcgen05.mma.cta_group::2 (launched with cluster size 2)
   int tma_epi, nbuf, nbuf_log2, nsb;  // bf16 outputs: epilogue staged through `nbuf` (2/4/8) smem boxes, `nsb` 64-column blocks/tile
-  bf16* pool_out; int pool_cs, pool_coff; unsigned short* pool_idx;  // fused 2x2 max-pool (ConvEpilogue::pool_out)
+  bf16* pool_out; int pool_cs, pool_coff; unsigned short* pool_idx; int pool_keep_full;  // fused 2x2 max-pool (ConvEpilogue)
 };
 
 // kMode: 1 / 2 / 4 = K blocks (one tap x 64 channels) per pipeline stage; 3 = column-box mode for 3x3 pad-1 layers:
@@ -399,6 +399,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       ea.out_W = p.out_W; ea.out_H = p.out_H; ea.rng = p.rng; ea.rng_channels = p.rng_channels;
       ea.csum = csum;
       ea.pool_out = p.pool_out; ea.pool_cs = p.pool_cs; ea.pool_coff = p.pool_coff; ea.pool_idx = p.pool_idx;
+      ea.pool_keep_full = p.pool_keep_full;
       const int my_tiles = u0 < total ? (total - 1 - u0) / ustep + 1 : 0;
       auto tile_of = [&](int it, int& nt, int& w0, int& h0, int& n0) {
         DBX_UNIT_TILE(u0 + it * ustep, nt_, mt_);
@@ -644,7 +645,7 @@ int conv_fprop(const Act& x, const void* wk, int R, int S, int pad, const Act& o
                     out.H % 2 == 0 && out.W % 2 == 0 && epi.pool_cs % 8 == 0 && epi.pool_coff % 8 == 0;
     if (ok) {
       p.pool_out = (bf16*)epi.pool_out; p.pool_cs = epi.pool_cs; p.pool_coff = epi.pool_coff;
-      p.pool_idx = (unsigned short*)epi.pool_idx;
+      p.pool_idx = (unsigned short*)epi.pool_idx; p.pool_keep_full = epi.pool_keep_full;
     } else {
       pool_after = true;  // same result from the stand-alone kernel behind this launch (which then stores `out`)
     }

@@ -366,10 +366,12 @@ struct Net {
   }
   // conv + bias + ReLU + 2x2 max-pool in one launch (ConvEpilogue::pool_out): `pooled` and the arg-max map are
   // written, the full-resolution activation `full` only when the launch has to fall back to the stand-alone pool.
-  int conv_pool(const Act& x, const char* grp, const Act& full, const Act& pooled, void* idx, cudaStream_t st) {
+  int conv_pool(const Act& x, const char* grp, const Act& full, const Act& pooled, void* idx, cudaStream_t st,
+                bool keep_full = false) {
     ConvEpilogue e;
     e.bias = bias_of(grp); e.relu = 1;
     e.pool_out = pooled.ptr; e.pool_cs = pooled.cs; e.pool_coff = pooled.coff; e.pool_idx = idx;
+    e.pool_keep_full = keep_full ? 1 : 0;
     DBX_K((std::string("fprop:") + grp).c_str(), 2.0 * pixels(full) * macs_of(grp),
           conv_fprop(x, wk_of(grp), 3, 3, 1, full, e, 0, st));
     return DBX_OK;
@@ -473,8 +475,12 @@ struct Net {
     }
     DBX_TRY(conv(p2, "conv3_1", 3, 1, a31, true, nullptr, 0, 0, false, 0, st));
     DBX_TRY(conv(a31, "conv3_2", 3, 1, a32, true, nullptr, 0, 0, false, 0, st));
-    DBX_TRY(conv(a32, "conv3_4", 3, 1, a34, true, nullptr, 0, 0, false, 0, st));  // conv3_3 skipped (:193-195)
-    DBX_K("pool_fwd", 0.0, maxpool2x2_fwd(a34, p3, st));
+    if (pool_fuse) {  // conv3_3 skipped (:193-195); conv3_4 feeds the fusion buffer AND pool3
+      DBX_TRY(conv_pool(a32, "conv3_4", a34, p3, nullptr, st, true));
+    } else {
+      DBX_TRY(conv(a32, "conv3_4", 3, 1, a34, true, nullptr, 0, 0, false, 0, st));
+      DBX_K("pool_fwd", 0.0, maxpool2x2_fwd(a34, p3, st));
+    }
     DBX_TRY(conv(p3, "conv4_1", 3, 1, a41, true, nullptr, 0, 0, false, 0, st));
     DBX_TRY(conv(a41, "conv4_2", 3, 1, a42, true, nullptr, 0, 0, false, 0, st));
     DBX_TRY(conv(a42, "conv4_3", 3, 1, a43, true, nullptr, 0, 0, false, 0, st));

@@ -139,6 +139,7 @@ def _fwd_bwd(fuse_pool):
         eng = next(iter(net._engines.values()))
         N = 3
         pooled = [eng.buffer("p1", torch.bfloat16, (N, 120, 120, 64)).clone(), eng.buffer("p2", torch.bfloat16, (N, 60, 60, 128)).clone(),
+                  eng.buffer("p3", torch.bfloat16, (N, 30, 30, 256)).clone(), eng.buffer("fusion", torch.bfloat16).clone(),
                   eng.buffer("pi1", torch.int16).clone(), eng.buffer("pi2", torch.int16).clone()]
         score, loc, lm, rf = outs
         L = densebox_loss(score, loc, lab["bbox"], rand_neg_idx=rand, lm=lm, rf=rf, vertices=lab["vertices"],
