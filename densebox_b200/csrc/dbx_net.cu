@@ -687,11 +687,15 @@ struct Net {
     return (int)cudaMemsetAsync(G32(), 0, flat_n * 4, st);
   }
 
-  int sgd(float lr, float momentum, float wd, cudaStream_t st) {
+  // part: -1 = every parameter; 0 = gradient buckets 0 and 1 ([0, tail_off)); 1 = the last bucket ([tail_off, flat_n)).
+  // A data-parallel caller updates part 0 while the all-reduce of the last bucket is still in flight, then part 1.
+  int sgd(float lr, float momentum, float wd, cudaStream_t st, int part = -1) {
     if (!train) return DBX_ERR_STATE;
-    DBX_K("sgd", 0.0, sgd_step(W32(), G32(), V32(), WK(), flat_n, lr, momentum, wd, sgd_steps == 0 ? 1 : 0, 1, st));
-    ++sgd_steps;
-    dgrad_stale = true;
+    if (part < -1 || part > 1) return DBX_ERR_ARG;
+    const size_t lo = part == 1 ? tail_off : 0, hi = part == 0 ? tail_off : flat_n;
+    DBX_K("sgd", 0.0, sgd_step(W32() + lo, G32() + lo, V32() + lo, WK() + lo, hi - lo, lr, momentum, wd,
+                               sgd_steps == 0 ? 1 : 0, 1, st));
+    if (part != 0) { ++sgd_steps; dgrad_stale = true; }
     return DBX_OK;
   }
 };
@@ -870,6 +874,10 @@ int dbx_net_profile_get(void* handle, int i, char* tag, int tag_bytes, double* f
 int dbx_net_sgd_step(void* handle, float lr, float momentum, float weight_decay, void* stream) {
   if (!handle) return DBX_ERR_ARG;
   return ((Net*)handle)->sgd(lr, momentum, weight_decay, (cudaStream_t)stream);
+}
+int dbx_net_sgd_step_part(void* handle, int part, float lr, float momentum, float weight_decay, void* stream) {
+  if (!handle || part < 0 || part > 1) return DBX_ERR_ARG;
+  return ((Net*)handle)->sgd(lr, momentum, weight_decay, (cudaStream_t)stream, part);
 }
 
 }  // extern "C"

@@ -257,6 +257,11 @@ class NetEngine:
         check(lib().dbx_net_sgd_step(self.h, c_float(lr), c_float(momentum), c_float(weight_decay), stream_ptr()),
               "net_sgd_step")
 
+    def sgd_step_part(self, part, lr, momentum=0.9, weight_decay=5e-8):
+        """part 0 = gradient buckets 0 + 1, part 1 = the last bucket: see dbx_net_sgd_step_part."""
+        check(lib().dbx_net_sgd_step_part(self.h, c_int(part), c_float(lr), c_float(momentum), c_float(weight_decay),
+                                          stream_ptr()), "net_sgd_step_part")
+
     def flat_grads(self):
         return self.buffer("g32", torch.float32)
 

@@ -52,7 +52,7 @@ class DenseBoxTrainer:
     def __init__(self, net, batch_size, lr=1e-9, momentum=0.9, weight_decay=5e-8, lambda_loc=3.0, lambda_det=1.0,
                  lambda_lm=0.5, patch=240, rand_width=256, process_group=None, use_cuda_graph=True, dropout=True,
                  device=None, seed=0, allreduce_loss=False, nccl_max_ctas=8, count_exchange="peer", input_u8=False,
-                 mean=None, std=None):
+                 mean=None, std=None, reserve_stages=(1, 2), staged=False, sm_reserve=None):
         """input_u8=True: `step()` / `prefetch()` take the batch as decoded image bytes, uint8 [B,patch,patch,3]
         (densebox_b200.data.load_patch_u8), and ToTensor + Normalize(mean, std) (DenseBox.py:766-772) happen inside
         the first kernel — a quarter of the host->device bytes of the fp32 [B,3,patch,patch] form."""
@@ -65,7 +65,7 @@ class DenseBoxTrainer:
         self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
         self.rank = torch.distributed.get_rank(process_group) if process_group is not None else 0
         self.allreduce_loss = bool(allreduce_loss) and self.world > 1
-        self.pg_overlap, self.sm_reserve = self.pg, 0
+        self.pg_overlap, self.sm_reserve, self.reserve_stages = self.pg, 0, tuple(reserve_stages)
         if self.world > 1 and nccl_max_ctas and torch.distributed.get_backend(process_group) == "nccl":
             try:  # a second communicator whose kernels occupy at most `nccl_max_ctas` SMs (ncclConfig_t.maxCTAs)
                 opts = torch.distributed.ProcessGroupNCCL.Options()
@@ -76,6 +76,9 @@ class DenseBoxTrainer:
                 self.sm_reserve = (int(nccl_max_ctas) + 1) // 2 * 2
             except Exception:  # older torch / NCCL without per-communicator config: plain overlap, no reservation
                 self.pg_overlap, self.sm_reserve = self.pg, 0
+        self.staged = bool(staged)   # measurement aid: run the data-parallel step structure on one GPU
+        if sm_reserve is not None:
+            self.sm_reserve = int(sm_reserve)
         self.dropout = dropout
         # independent dropout streams per rank (the reference's nn.Dropout draws per process): fold the rank in
         self.seed = (seed ^ (self.rank * 0x9E3779B97F4A7C15)) & 0x7FFFFFFFFFFFFFFF if self.world > 1 else seed
@@ -285,8 +288,11 @@ class DenseBoxTrainer:
             self._loss(s, clamp_lm)
             e.backward_stage(0)
 
-        parts = (fwd, lb0, lambda: self._reserved(lambda: e.backward_stage(1)),
-                 lambda: self._reserved(lambda: e.backward_stage(2)))
+        def stage(i):
+            return (lambda: self._reserved(lambda: e.backward_stage(i))) if i in self.reserve_stages \
+                else (lambda: e.backward_stage(i))
+
+        parts = (fwd, lb0, stage(1), stage(2))
         key = (k, clamp_lm)
         if graph_ok and key not in self._graphs:  # capture before any collective of this step is in flight
             gs = []
@@ -296,9 +302,11 @@ class DenseBoxTrainer:
                     fn()
                 gs.append(g)
             self._graphs[key] = tuple(gs)
-        comm = not self._skip_allreduce
+        comm = not self._skip_allreduce and self.world > 1
         sk = self._skip_mask
-        if self._slots is not None:  # peer stores, no collective (runs in measurement modes too: the loss waits for it)
+        if self.world == 1:
+            pass  # staged single-GPU measurement: the loss kernel counts its own batch
+        elif self._slots is not None:  # peer stores, no collective (runs in measurement modes too: the loss waits for it)
             check(lib().dbx_count_exchange(ptr(s["bbox"]), ptr(s["labels"]), c_int(self.B), self._peer_ptrs,
                                            c_int(self.world), c_int(self.rank), ptr(self._slots), stream_ptr()),
                   "count_exchange")
@@ -319,20 +327,16 @@ class DenseBoxTrainer:
         if comm and not sk & 4:
             works.append(dist.all_reduce(e.grad_bucket(1), group=self.pg_overlap, async_op=True))
         run[3]()
+        w_tail = None
         if comm and not sk & 8:
-            works.append(dist.all_reduce(e.grad_bucket(2), group=self.pg, async_op=True))  # exposed: full-speed group
+            w_tail = dist.all_reduce(e.grad_bucket(2), group=self.pg, async_op=True)  # exposed: full-speed group
         for w in works:
             w.wait()
-        if graph_ok:
-            g = self._graph_sgd.get(self.lr)
-            if g is None:
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, capture_error_mode="thread_local"):
-                    e.sgd_step(self.lr, self.momentum, self.weight_decay)
-                self._graph_sgd[self.lr] = g
-            g.replay()
-        else:
-            e.sgd_step(self.lr, self.momentum, self.weight_decay)
+        # SGD of buckets 0 + 1 (96 % of the parameters) runs while the last bucket is still being reduced
+        e.sgd_step_part(0, self.lr, self.momentum, self.weight_decay)
+        if w_tail is not None:
+            w_tail.wait()
+        e.sgd_step_part(1, self.lr, self.momentum, self.weight_decay)
 
     def step(self, x, bbox, vertices=None, labels=None, rand_neg_idx=None, lm_rand_neg_idx=None, async_loss=False):
         """x [B,3,240,240] fp32 (host pinned or device), labels in 60-space.  Returns the loss of this rank's shard
@@ -356,7 +360,7 @@ class DenseBoxTrainer:
             self._staged = None  # a prefetch that was not consumed is dropped (its key can never match stale memory)
             clamp_lm = labels is not None  # `_pn` helpers of train_densebox_online (:1899-1907)
             graph_ok = self.use_graph and self.step_no >= 1  # step 0 runs eagerly (one-time inits, SGD first-step flag)
-            if self.world > 1:
+            if self.world > 1 or self.staged:
                 self._step_dp(k, clamp_lm, graph_ok)
             else:
                 self._step_single(k, clamp_lm, graph_ok)

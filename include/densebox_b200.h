@@ -209,6 +209,10 @@ int dbx_net_zero_grad(void* handle, void* stream);                       /* opti
 /* optimizer.step() — torch.optim.SGD(momentum, weight_decay) :2821-2824, :2926; also clears g32 and refreshes the
  * bf16 filters. */
 int dbx_net_sgd_step(void* handle, float lr, float momentum, float weight_decay, void* stream);
+/* The same update in two launches for data-parallel callers: part 0 = gradient buckets 0 and 1, part 1 = the last
+ * bucket (conv1/conv2 filters + biases).  Part 0 runs while the all-reduce of the last bucket is still in flight;
+ * call part 0 then part 1, once each per step. */
+int dbx_net_sgd_step_part(void* handle, int part, float lr, float momentum, float weight_decay, void* stream);
 
 /* Measurement aids: per-launch CUDA-event timing of the engine's own kernels (eager mode; synchronise before
  * reading) and the number of kernel launches issued so far.  tags: "fprop:<layer>", "dgrad:<layer>",
