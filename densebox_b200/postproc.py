@@ -40,10 +40,11 @@ def decode_nms(score_map, loc_map, lm_loc_map=None, K=10, nms_thresh=0.4, lm_hea
     l = _strides(loc_map)
     m = _strides(lm_loc_map) if lm_loc_map is not None else (0, 0, 0)
     fn = lib().dbx_decode_nms_heat if heat else lib().dbx_decode_nms
-    check(fn(ptr(score_map), c_long(s_img), c_long(s_pix), ptr(loc_map), c_long(l[0]), c_long(l[1]),
-             c_long(l[2]), ptr(lm_loc_map), c_long(m[0]), c_long(m[1]), c_long(m[2]), c_int(N),
-             c_int(h), c_int(w), c_int(K), ctypes.c_double(nms_thresh), ptr(dets), ptr(keep),
-             stream_ptr()), "decode_nms")
+    with torch.cuda.device(score_map.device):
+        check(fn(ptr(score_map), c_long(s_img), c_long(s_pix), ptr(loc_map), c_long(l[0]), c_long(l[1]),
+                 c_long(l[2]), ptr(lm_loc_map), c_long(m[0]), c_long(m[1]), c_long(m[2]), c_int(N),
+                 c_int(h), c_int(w), c_int(K), ctypes.c_double(nms_thresh), ptr(dets), ptr(keep),
+                 stream_ptr()), "decode_nms")
     dets, keep = dets.cpu().numpy().astype(np.float64), keep.cpu().numpy().astype(bool)
     ncol = 13 if lm_loc_map is not None else 5
     return [dets[i][keep[i]][:, :ncol] for i in range(N)]

@@ -382,13 +382,3 @@ class DenseBoxTrainer:
                 ev = self._loss_events[j] = torch.cuda.Event()
             ev.record(cur)
             return PendingLoss(out, self._loss_host[j], ev)
-
-    def kernels_per_step(self):
-        """Number of this library's kernel launches in one training step (for bench.py's gpu_launches)."""
-        convs = 13 + (3 if self.variant != "densebox" else 0)          # fprop
-        fwd = 1 + convs + 3 + 1 + (2 if self.variant != "densebox" else 0)  # im2col, convs, pools, upsample, refine glue
-        dgrads = convs - 1
-        wgrads = convs * 2                                               # wgrad + bias colsum
-        bwd = dgrads + wgrads + 3 + 1 + 1 + (2 if self.variant != "densebox" else 0)
-        sgd = 1 + (convs - 1)
-        return fwd + 1 + bwd + sgd + (1 if self.dropout else 0) + (1 if self.world > 1 else 0)
