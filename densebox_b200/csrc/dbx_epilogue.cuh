@@ -39,6 +39,9 @@ struct EpiArgs {
   int pool_cs = 0, pool_coff = 0;
   unsigned short* pool_idx = nullptr;   // 2-bit arg-max map (u16 per pooled pixel and 8 channels) or null
   int pool_keep_full = 0;               // also stage + TMA-store the full-resolution tile
+  bf16* unpool_out = nullptr;           // fused max-pool backward: full-resolution gradient view (ConvEpilogue::unpool_out)
+  int unpool_cs = 0, unpool_coff = 0;
+  const unsigned short* unpool_idx = nullptr;
 };
 
 __device__ __forceinline__ uint32_t bf162_as_u32(__nv_bfloat162 h) { return *reinterpret_cast<uint32_t*>(&h); }
@@ -239,6 +242,37 @@ __device__ __forceinline__ void epilogue_tma(const EpiArgs& e, const CUtensorMap
           for (int g = 0; g < 4; ++g)
             *reinterpret_cast<uint4*>(sb + chunk[g]) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
           }
+          if (e.unpool_out) {
+            // fused max-pool backward: this row is a POOLED pixel; its (already ReLU-masked) gradient goes to the
+            // arg-max position of its 2 x 2 window of the full-resolution gradient, zeros to the other three.  The
+            // staged copy above only feeds the column sums; it is not stored.
+            const int px = w0 + r_w, py = h0 + r_h;
+            if (px < e.out_W && py < e.out_H) {
+              const size_t pp = ((size_t)(n0 + r_n) * e.out_H + py) * e.out_W + px;
+              const uint2 ib = __ldg(reinterpret_cast<const uint2*>(e.unpool_idx + pp * (e.cout >> 3) + (ch >> 3)));
+              const size_t fw = (size_t)e.out_W * 2;
+              bf16* o00 = e.unpool_out + (((size_t)(n0 + r_n) * e.out_H * 2 + 2 * py) * fw + 2 * px) * e.unpool_cs +
+                          e.unpool_coff + ch;
+#pragma unroll
+              for (int pos = 0; pos < 4; ++pos) {
+                uint4* op = reinterpret_cast<uint4*>(o00 + ((size_t)(pos >> 1) * fw + (pos & 1)) * e.unpool_cs);
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                  const uint32_t b16 = ((g < 2 ? ib.x : ib.y) >> (16 * (g & 1))) & 0xFFFFu;  // 2 arg bits x 8 channels
+                  const uint32_t x = b16 ^ (uint32_t)(pos * 0x5555);
+                  const uint32_t z = ~(x | (x >> 1)) & 0x5555u;                               // bit 2j: channel j hit
+                  uint32_t w[4];
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {
+                    const uint32_t t = z >> (4 * i);
+                    const uint32_t m = ((0u - (t & 1u)) & 0x0000FFFFu) | ((0u - ((t >> 2) & 1u)) & 0xFFFF0000u);
+                    w[i] = pk[4 * g + i] & m;
+                  }
+                  op[g] = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+              }
+            }
+          }
         }
       } else {
         // ---- ragged tail (block_n not a multiple of 64): 16 columns at a time, scalar guards
@@ -300,7 +334,7 @@ __device__ __forceinline__ void epilogue_tma(const EpiArgs& e, const CUtensorMap
         }
       }
       named_bar_sync(1, 256);
-      if (leader) {
+      if (leader && !e.unpool_out) {
         tma_store_4d(tmO, sb, nt * e.block_n + j * 64, w0, h0, n0);
         bulk_commit();
       }

@@ -175,6 +175,7 @@ struct FpropParams {
   int cta2;                // 1: CTA pairs drive tcgen05.mma.cta_group::2 (launched with cluster size 2)
   int tma_epi, nbuf, nbuf_log2, nsb;  // bf16 outputs: epilogue staged through `nbuf` (2/4/8) smem boxes, `nsb` 64-column blocks/tile
   bf16* pool_out; int pool_cs, pool_coff; unsigned short* pool_idx; int pool_keep_full;  // fused 2x2 max-pool (ConvEpilogue)
+  bf16* unpool_out; int unpool_cs, unpool_coff; const unsigned short* unpool_idx;        // fused max-pool backward
 };
 
 // kMode: 1 / 2 / 4 = K blocks (one tap x 64 channels) per pipeline stage; 3 = column-box mode for 3x3 pad-1 layers:
@@ -400,6 +401,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       ea.csum = csum;
       ea.pool_out = p.pool_out; ea.pool_cs = p.pool_cs; ea.pool_coff = p.pool_coff; ea.pool_idx = p.pool_idx;
       ea.pool_keep_full = p.pool_keep_full;
+      ea.unpool_out = p.unpool_out; ea.unpool_cs = p.unpool_cs; ea.unpool_coff = p.unpool_coff; ea.unpool_idx = p.unpool_idx;
       const int my_tiles = u0 < total ? (total - 1 - u0) / ustep + 1 : 0;
       auto tile_of = [&](int it, int& nt, int& w0, int& h0, int& n0) {
         DBX_UNIT_TILE(u0 + it * ustep, nt_, mt_);
@@ -501,8 +503,30 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 }
 
 
+static int conv_fprop_impl(const Act& x, const void* wk, int R, int S, int pad, const Act& out, const ConvEpilogue& epi,
+                           int block_n, cudaStream_t stream, bool* unpool_fused);
+
 int conv_fprop(const Act& x, const void* wk, int R, int S, int pad, const Act& out, const ConvEpilogue& epi,
                int block_n, cudaStream_t stream) {
+  if (!epi.unpool_out) return conv_fprop_impl(x, wk, R, S, pad, out, epi, block_n, stream, nullptr);
+  // fused max-pool backward wanted: try it; if the launch cannot fuse (tile shape, no room for the column sums),
+  // fall back to the plain data gradient followed by the stand-alone un-pooling kernel
+  if (epi.aux_mode != 1 || !epi.aux || !epi.unpool_idx) return DBX_ERR_ARG;
+  bool fused = false;
+  int rc = conv_fprop_impl(x, wk, R, S, pad, out, epi, block_n, stream, &fused);
+  if (rc || fused) return rc;
+  ConvEpilogue plain = epi;
+  plain.aux = nullptr; plain.aux_mode = 0; plain.aux_cs = 0; plain.aux_coff = 0; plain.colsum = nullptr;
+  plain.unpool_out = nullptr; plain.unpool_idx = nullptr;
+  rc = conv_fprop_impl(x, wk, R, S, pad, out, plain, block_n, stream, nullptr);
+  if (rc) return rc;
+  Act p = out; p.ptr = const_cast<void*>(epi.aux); p.cs = epi.aux_cs; p.coff = epi.aux_coff;
+  Act dy = out; dy.ptr = epi.unpool_out; dy.H = out.H * 2; dy.W = out.W * 2; dy.cs = epi.unpool_cs; dy.coff = epi.unpool_coff;
+  return maxpool2x2_bwd_idx(p, out, epi.unpool_idx, dy, stream, epi.colsum);
+}
+
+static int conv_fprop_impl(const Act& x, const void* wk, int R, int S, int pad, const Act& out, const ConvEpilogue& epi,
+                           int block_n, cudaStream_t stream, bool* unpool_fused) {
   if (!x.ptr || !wk || !out.ptr) return DBX_ERR_ARG;
   if (x.C % 64 || out.C % 16) return DBX_ERR_ARG;
   if (out.H != x.H + 2 * pad - R + 1 || out.W != x.W + 2 * pad - S + 1 || out.N != x.N) return DBX_ERR_ARG;
@@ -649,6 +673,16 @@ int conv_fprop(const Act& x, const void* wk, int R, int S, int pad, const Act& o
     } else {
       pool_after = true;  // same result from the stand-alone kernel behind this launch (which then stores `out`)
     }
+  }
+
+  if (epi.unpool_out) {
+    const bool ok = colbox && tma_epi && epi.aux_mode == 1 && block_n % 64 == 0 && out.C % 64 == 0 &&
+                    epi.unpool_cs % 8 == 0 && epi.unpool_coff % 8 == 0 && (!epi.colsum || p.colsum) && !pool_after &&
+                    !epi.pool_out;
+    if (!ok) { if (unpool_fused) *unpool_fused = false; return DBX_OK; }  // nothing launched: the caller falls back
+    p.unpool_out = (bf16*)epi.unpool_out; p.unpool_cs = epi.unpool_cs; p.unpool_coff = epi.unpool_coff;
+    p.unpool_idx = (const unsigned short*)epi.unpool_idx;
+    if (unpool_fused) *unpool_fused = true;
   }
 
   if (p.kps == 3) p.kps = 2;
