@@ -160,6 +160,9 @@ int sgd_step(float* w, float* g, float* v, void* wb, size_t n, float lr, float m
              int zero_grad, cudaStream_t st);
 int cast_bf16(const float* src, void* dst, size_t n, cudaStream_t st);
 int blockdiag_mask(float* g, int rows, int ld, int nh, const int* start, cudaStream_t st);
+// conv5_2 o conv5_1 as one matrix (inference only; see heads_fold_kernel): wf bf16 [HC][768], bf fp32 [HC]
+int heads_fold(const float* w1, int ld1, const float* b1, const float* w2, int ld2, const float* b2, const int* start,
+               int nh, int HC, void* wf, float* bf, cudaStream_t st);
 int dropout_mask(void* mask, size_t n, unsigned long long seed, unsigned long long offset, cudaStream_t st);
 int refine_pool_pack(const float* head, int HC, void* pooled, int N, int H, int W, cudaStream_t st);
 int refine_pool_bwd(const float* head, int HC, const void* dpooled, void* dhead, int N, int H, int W, cudaStream_t st);

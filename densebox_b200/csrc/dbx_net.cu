@@ -203,6 +203,8 @@ struct Net {
     add_buf("a44", px8 * 512 * 2);
     add_buf("hd", px4 * 512 * nh * 2);
     add_buf("head_out", px4 * HC * 4);
+    add_buf("wfold", (size_t)HC * 768 * 2);   // inference: conv5_2 o conv5_1 as one [HC][768] matrix (heads_fold)
+    add_buf("bfold", 256);
     const int h4 = H / 4, w4 = W / 4, h8 = H / 8, w8 = W / 8;
     if (variant >= 1) {
       add_buf("rp", px8 * 64 * 2);
@@ -493,14 +495,27 @@ struct Net {
       rng_host[0] = seed; rng_host[1] = offset;
       DBX_TRY((int)cudaMemcpyAsync(buf("rng"), rng_host, 16, cudaMemcpyHostToDevice, st));
     }
-    {
+    // Inference nets without dropout: the reference puts nothing but Dropout between conv5_1_* and conv5_2_*
+    // (DenseBox.py:158-178), so the two 1x1 convolutions are ONE 768 -> HC matrix; the 512-channel hidden maps are
+    // never computed, let alone stored.  Folded from the fp32 masters on every forward (a few microseconds).
+    bool fold = !train && dropout_mode == 0;
+    { const char* e = ab_env("DBX_HEADS_FOLD"); if (e && e[0] == '0') fold = false; }
+    if (fold) {
+      const Group& g1 = groups[group_id("heads1")];
+      const Group& g2 = groups[group_id("heads2")];
+      DBX_K("heads_fold", 0.0, heads_fold(W32() + g1.w_off, g1.ld, bias_of("heads1"), W32() + g2.w_off, g2.ld,
+                                          bias_of("heads2"), ch_start, nh, HC, buf("wfold"), (float*)buf("bfold"), st));
+      ConvEpilogue e;
+      e.bias = (const float*)buf("bfold"); e.out_fp32 = 1;
+      DBX_K("fprop:heads_folded", 2.0 * pixels(ho) * 768.0 * HC, conv_fprop(fus, buf("wfold"), 1, 1, 0, ho, e, 0, st));
+    } else {
       ConvEpilogue e;
       e.bias = bias_of("heads1");
       if (dropout_mode == 2) { e.aux = buf("drop"); e.aux_cs = 512 * nh; e.aux_mode = 2; e.epi_bufs = 4; }
       else if (dropout_mode) { e.aux_mode = 3; e.rng = (const unsigned long long*)buf("rng"); e.rng_channels = 512 * nh; }
       DBX_K("fprop:heads1", 2.0 * pixels(hd) * macs_of("heads1"), conv_fprop(fus, wk_of("heads1"), 1, 1, 0, hd, e, 0, st));
     }
-    DBX_TRY(conv(hd, "heads2", 1, 0, ho, false, nullptr, 0, 0, true, 0, st));
+    if (!fold) DBX_TRY(conv(hd, "heads2", 1, 0, ho, false, nullptr, 0, 0, true, 0, st));
     if (variant >= 1) {
       Act rp = act("rp", h8, w8, 64), r1 = act("r1", h8 - 2, w8 - 2, 64), r2 = act("r2", h8 - 6, w8 - 6, 64);
       Act rup = act("rup", h4, w4, 64), rf = act("rf_out", h4, w4, 16);
