@@ -584,36 +584,48 @@ __global__ void __launch_bounds__(256) colsum_kernel(Act dy, float* __restrict__
 // ---- conv5_2 o conv5_1 folded into one 768 -> HC matrix (inference: no dropout, and the reference has no
 // non-linearity between the two 1x1 convolutions, DenseBox.py:158-178): wf[o][k] = sum_c w2[o][c] w1[c][k] over the 512
 // hidden channels c of the branch that owns output o, bf[o] = b2[o] + sum_c w2[o][c] b1[c].  fp32 masters in, bf16
-// GEMM operand + fp32 bias out.  Grid (HC, 4): y < 3 -> 256 columns k each, y == 3 -> the bias.
+// GEMM operand + fp32 bias out.  Grid (HC, 25): y < 24 -> 32 columns k (lane) x 8 slices of the hidden channels (warp),
+// 64 dependent-free FMAs per thread in batches of 8 loads (the kernel is pure load latency), summed in shared memory
+// in a fixed order; y == 24 -> the bias.
 struct FoldStarts { int s[5]; };
-__global__ void heads_fold_kernel(const float* __restrict__ w1, int ld1, const float* __restrict__ b1,
-                                  const float* __restrict__ w2, int ld2, const float* __restrict__ b2, FoldStarts st,
-                                  int nh, bf16* __restrict__ wf, float* __restrict__ bf) {
-  const int o = blockIdx.x;
+__global__ void __launch_bounds__(256)
+heads_fold_kernel(const float* __restrict__ w1, int ld1, const float* __restrict__ b1, const float* __restrict__ w2,
+                  int ld2, const float* __restrict__ b2, FoldStarts st, int nh, bf16* __restrict__ wf,
+                  float* __restrict__ bf) {
+  __shared__ float red[8][32];
+  const int o = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int b = -1;
   for (int i = 0; i < nh; ++i)
     if (o >= st.s[i] && o < st.s[i + 1]) b = i;
   const float* w2r = w2 + (size_t)o * ld2 + 512 * (b < 0 ? 0 : b);
-  if (blockIdx.y < 3) {
-    const int k = blockIdx.y * 256 + threadIdx.x;
-    float a = 0.f;
+  float a = 0.f;
+  if (blockIdx.y < 24) {
+    const int k = blockIdx.y * 32 + lane;
     if (b >= 0) {
-      const float* w1c = w1 + (size_t)512 * b * ld1 + k;
-      for (int c = 0; c < 512; ++c) a = fmaf(__ldg(w2r + c), __ldg(w1c + (size_t)c * ld1), a);
+      const float* w1c = w1 + ((size_t)512 * b + 64 * warp) * ld1 + k;
+#pragma unroll 8
+      for (int c = 0; c < 64; ++c) a = fmaf(__ldg(w2r + 64 * warp + c), __ldg(w1c + (size_t)c * ld1), a);
     }
-    wf[(size_t)o * ld1 + k] = __float2bfloat16(a);
+    red[warp][lane] = a;
+    __syncthreads();
+    if (warp == 0) {
+      float v = 0.f;
+#pragma unroll
+      for (int g = 0; g < 8; ++g) v += red[g][lane];
+      wf[(size_t)o * ld1 + k] = __float2bfloat16(v);
+    }
   } else {
-    __shared__ float red[256];
-    float a = 0.f;
     if (b >= 0)
       for (int c = threadIdx.x; c < 512; c += 256) a = fmaf(__ldg(w2r + c), __ldg(b1 + 512 * b + c), a);
-    red[threadIdx.x] = a;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) a += __shfl_xor_sync(0xffffffffu, a, d);
+    if (lane == 0) red[warp][0] = a;
     __syncthreads();
-    for (int s2 = 128; s2 > 0; s2 >>= 1) {
-      if ((int)threadIdx.x < s2) red[threadIdx.x] += red[threadIdx.x + s2];
-      __syncthreads();
+    if (threadIdx.x == 0) {
+      float v = b >= 0 ? __ldg(b2 + o) : 0.f;
+      for (int g = 0; g < 8; ++g) v += red[g][0];
+      bf[o] = v;
     }
-    if (threadIdx.x == 0) bf[o] = (b >= 0 ? __ldg(b2 + o) : 0.f) + red[0];
   }
 }
 
@@ -622,7 +634,7 @@ int heads_fold(const float* w1, int ld1, const float* b1, const float* w2, int l
   if (!w1 || !b1 || !w2 || !b2 || !start || !wf || !bf || ld1 != 768 || nh < 1 || nh > 4 || HC < 1) return DBX_ERR_ARG;
   FoldStarts fs;
   for (int i = 0; i < 5; ++i) fs.s[i] = start[i];
-  heads_fold_kernel<<<dim3(HC, 4), 256, 0, st>>>(w1, ld1, b1, w2, ld2, b2, fs, nh, (bf16*)wf, bf);
+  heads_fold_kernel<<<dim3(HC, 25), 256, 0, st>>>(w1, ld1, b1, w2, ld2, b2, fs, nh, (bf16*)wf, bf);
   return (int)cudaGetLastError();
 }
 

@@ -2,6 +2,7 @@
 reference (DenseBox.py:3114-3217, :3220-3300, :3398-3443) for a whole batch in one kernel launch (the reference
 handles one image at a time on the CPU)."""
 import ctypes
+import threading
 
 import numpy as np
 import torch
@@ -34,8 +35,10 @@ def decode_nms(score_map, loc_map, lm_loc_map=None, K=10, nms_thresh=0.4, lm_hea
     N, _, h, w = score_map.shape
     for t in (score_map, loc_map, lm_loc_map):
         assert t is None or (t.dtype == torch.float32 and t.is_cuda)
-    dets = torch.empty(N, K, 13, dtype=torch.float32, device=score_map.device)
-    keep = torch.empty(N, K, dtype=torch.int32, device=score_map.device)
+    # one device buffer, one pinned host buffer, ONE device->host copy: rows [N, K, 13] fp32 followed by keep [N, K] int32
+    nd = N * K * 13
+    out = torch.empty(nd + N * K, dtype=torch.float32, device=score_map.device)
+    dets, keep = out[:nd], out[nd:].view(torch.int32)
     s_img, s_pix, _ = _strides(score_map)
     l = _strides(loc_map)
     m = _strides(lm_loc_map) if lm_loc_map is not None else (0, 0, 0)
@@ -45,9 +48,27 @@ def decode_nms(score_map, loc_map, lm_loc_map=None, K=10, nms_thresh=0.4, lm_hea
                  c_long(l[2]), ptr(lm_loc_map), c_long(m[0]), c_long(m[1]), c_long(m[2]), c_int(N),
                  c_int(h), c_int(w), c_int(K), ctypes.c_double(nms_thresh), ptr(dets), ptr(keep),
                  stream_ptr()), "decode_nms")
-    dets, keep = dets.cpu().numpy().astype(np.float64), keep.cpu().numpy().astype(bool)
+    host = _pinned(out.numel(), score_map.device.index)
+    host.copy_(out, non_blocking=True)
+    torch.cuda.current_stream(score_map.device).synchronize()
+    hv = host.numpy()
     ncol = 13 if lm_loc_map is not None else 5
-    return [dets[i][keep[i]][:, :ncol] for i in range(N)]
+    rows = hv[:nd].reshape(N, K, 13)[:, :, :ncol].astype(np.float64)
+    alive = hv[nd:].view(np.int32).reshape(N, K) != 0
+    return [rows[i][alive[i]] for i in range(N)]
+
+
+_PINNED = {}
+
+
+def _pinned(n, dev):
+    """Page-locked staging buffer for the detections, cached per (thread, device, size); the rows are copied out of it
+    before decode_nms returns."""
+    key = (threading.get_ident(), dev, n)
+    t = _PINNED.get(key)
+    if t is None:
+        t = _PINNED[key] = torch.empty(n, dtype=torch.float32, pin_memory=True)
+    return t
 
 
 def perspective_matrix(src_pts):
