@@ -76,15 +76,6 @@ struct ConvEpilogue {
   int pool_cs = 0, pool_coff = 0;
   void* pool_idx = nullptr;
   int pool_keep_full = 0;      // 1: store the full-resolution output too (conv3_4: the fusion buffer needs it)
-  // The adjoint, for data-gradient launches whose output is the gradient of a POOLED map (dgrad of conv2_1 / conv3_1):
-  // instead of storing d(pooled), store its 2x2 un-pooling straight into the full-resolution gradient (view
-  // unpool_out: [N, 2H, 2W, C]) — the arg-max position of every window (unpool_idx, the map of maxpool2x2_fwd) gets
-  // (aux > 0 ? v : 0), the other three get 0; aux_mode must be 1 with aux = the pooled activation (its sign is the
-  // ReLU mask of the conv that fed the pool).  `colsum` then is the bias gradient of that conv.  Falls back to the
-  // plain launch + maxpool2x2_bwd_idx when the launch cannot use 8 x 16 column-box tiles.
-  void* unpool_out = nullptr;
-  int unpool_cs = 0, unpool_coff = 0;
-  const void* unpool_idx = nullptr;
   float* colsum = nullptr;     // fp32 [cout] or null: colsum[c] += sum over pixels of out[.., c] (as stored, bf16-rounded).
                                // A data-gradient launch uses it to produce the bias gradient of the layer below
                                // in its own epilogue instead of re-reading dY from HBM; requires bias == nullptr.

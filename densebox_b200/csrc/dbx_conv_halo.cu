@@ -35,6 +35,7 @@ struct HaloParams {
   float* colsum; int csum_off;  // fused bias gradient of the layer below (see ConvEpilogue::colsum)
 };
 
+template <bool kMask>   // epilogue flavour (dbx_epilogue.cuh): ReLU-backward / dropout mask tile, or bias + ReLU only
 __global__ void __launch_bounds__(kHaloThreads, 1)
 conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmX,
@@ -206,7 +207,8 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int rem = mt - n0 * (p.tiles_w * p.tiles_h), hq = p.fd_tw.div(rem);
       w0 = (rem - hq * p.tiles_w) * 8; h0 = hq * 16;
     };
-    epilogue_tma<false>(ea, &tmO, &tmX, ring, aux_bar, tfull_bar, tempty_bar, tmem, my_tiles, tile_of);
+    epilogue_tma<false, kMask ? kEpiMask : kEpiPlain>(ea, &tmO, &tmX, ring, aux_bar, tfull_bar, tempty_bar, tmem,
+                                                      my_tiles, tile_of);
   }
   tc_fence_before();
   __syncthreads();
@@ -287,8 +289,13 @@ int conv3x3_halo(const Act& x, const void* wk, const Act& out, const ConvEpilogu
   } else {
     tmX = tmO;
   }
-  static SmemAttrOnce attr_once;
-  { const int arc = set_max_smem_once((const void*)conv3x3_halo_kernel, kHaloSmem + 1024, &attr_once); if (arc) return arc; }
+  if (epi.aux_mode != 0 && epi.aux_mode != 1 && epi.aux_mode != 2) return DBX_ERR_ARG;
+  typedef void (*HaloFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const HaloParams);
+  static const HaloFn fns[2] = {conv3x3_halo_kernel<false>, conv3x3_halo_kernel<true>};
+  static SmemAttrOnce attr_once[2];
+  const int fi = epi.aux_mode ? 1 : 0;
+  const HaloFn fn = fns[fi];
+  { const int arc = set_max_smem_once((const void*)fn, kHaloSmem + 1024, &attr_once[fi]); if (arc) return arc; }
   const int total = p.m_tiles * p.n_tiles;
   const int grid = total < tensor_sms() ? total : tensor_sms();
   cudaLaunchConfig_t cfg{};
@@ -297,7 +304,7 @@ int conv3x3_halo(const Act& x, const void* wk, const Act& out, const ConvEpilogu
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  return (int)cudaLaunchKernelEx(&cfg, conv3x3_halo_kernel, tmA, tmB, tmO, tmX, p);
+  return (int)cudaLaunchKernelEx(&cfg, fn, tmA, tmB, tmO, tmX, p);
 }
 
 }  // namespace dbx

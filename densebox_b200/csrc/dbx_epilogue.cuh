@@ -39,9 +39,6 @@ struct EpiArgs {
   int pool_cs = 0, pool_coff = 0;
   unsigned short* pool_idx = nullptr;   // 2-bit arg-max map (u16 per pooled pixel and 8 channels) or null
   int pool_keep_full = 0;               // also stage + TMA-store the full-resolution tile
-  bf16* unpool_out = nullptr;           // fused max-pool backward: full-resolution gradient view (ConvEpilogue::unpool_out)
-  int unpool_cs = 0, unpool_coff = 0;
-  const unsigned short* unpool_idx = nullptr;
 };
 
 __device__ __forceinline__ uint32_t bf162_as_u32(__nv_bfloat162 h) { return *reinterpret_cast<uint32_t*>(&h); }
@@ -110,7 +107,14 @@ __device__ __forceinline__ void epi_dropout16(uint32_t* pk, uint32_t bits) {
 }
 
 // tile_of(it, nt, w0, h0, n0): CTA-local tile iteration -> output-channel tile and pixel-box origin.
-template <bool kCta2, class TileFn>
+// kEpi selects the epilogue flavour at compile time (kEpiPlain: bias / ReLU only; kEpiMask: ReLU-backward or dropout
+// mask tile prefetched by TMA, e.aux_mode 1 / 2; kEpiPhilox: dropout drawn in place, e.aux_mode 3; kEpiPool: fused
+// 2x2 max-pool).  The short-K layers (conv1_1, conv1_2, conv2_1, the heads) are paced by this code, two warps per
+// scheduler with every stall exposed: run-time tests of features a launch does not use (a parameter load, a compare
+// and a branch each, ~15 per sub-block) measurably slow ALL of them — the unused max-pool-backward path alone cost
+// 0.055 ms per step (profiles/README.md item 31).
+enum { kEpiPlain = 0, kEpiMask = 1, kEpiPhilox = 2, kEpiPool = 3 };
+template <bool kCta2, int kEpi, class TileFn>
 __device__ __forceinline__ void epilogue_tma(const EpiArgs& e, const CUtensorMap* tmO, const CUtensorMap* tmX,
                                              uint8_t* ring, uint64_t* aux_bar, uint64_t* tfull_bar,
                                              uint64_t* tempty_bar, uint32_t tmem, int my_tiles, TileFn tile_of) {
@@ -119,7 +123,7 @@ __device__ __forceinline__ void epilogue_tma(const EpiArgs& e, const CUtensorMap
   const int row = q4 * 32 + lane;
   const bool leader = threadIdx.x == 64;
   const int nsb = e.nsb, nbuf = 1 << e.nbuf_log2, nmask = nbuf - 1;
-  const bool aux_tma = e.aux_mode == 1 || e.aux_mode == 2;
+  constexpr bool aux_tma = kEpi == kEpiMask;
   const int D = aux_tma ? (nbuf >> 1) : 0;          // mask prefetch distance in sub-blocks
   const int total_sb = my_tiles * nsb;
   const uint32_t box_bytes = (uint32_t)e.box_rows * 128u;
@@ -146,10 +150,12 @@ __device__ __forceinline__ void epilogue_tma(const EpiArgs& e, const CUtensorMap
     for (int i = 0; i < D && a_q < total_sb; ++i) issue_aux_next();
 
   unsigned long long rng_seed = 0, rng_off = 0;
-  if (e.aux_mode == 3) { rng_seed = e.rng[0]; rng_off = e.rng[1]; }
+  if constexpr (kEpi == kEpiPhilox) { rng_seed = e.rng[0]; rng_off = e.rng[1]; }
   uint4 rnd = make_uint4(0u, 0u, 0u, 0u);
   unsigned long long rnd_ctr = ~0ull;
 
+  uint32_t ring_s = smem_u32(ring);
+  asm volatile("" : "+r"(ring_s));  // opaque: computed once, not re-derived per access
   int q = 0;
   for (int it = 0; it < my_tiles; ++it) {
     int nt, w0, h0, n0;
@@ -157,7 +163,7 @@ __device__ __forceinline__ void epilogue_tma(const EpiArgs& e, const CUtensorMap
     const int buf = it & 1; const uint32_t use = (uint32_t)(it >> 1);
     // element index of this row's channel 0 in the dropped activation (aux_mode 3)
     unsigned long long e_row = 0ull;
-    if (e.aux_mode == 3)
+    if constexpr (kEpi == kEpiPhilox)
       e_row = (((unsigned long long)(n0 + r_n) * e.out_H + (h0 + r_h)) * e.out_W + (w0 + r_w)) *
               (unsigned long long)e.rng_channels;
     mbar_wait(&tfull_bar[buf], use & 1);
@@ -165,6 +171,7 @@ __device__ __forceinline__ void epilogue_tma(const EpiArgs& e, const CUtensorMap
     const uint32_t taddr = tmem + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(buf * e.block_n);
     for (int j = 0; j < nsb; ++j, ++q) {
       uint8_t* sb = ring + (size_t)(q & nmask) * kEpiBox;
+      const uint32_t sb_s = ring_s + (uint32_t)(q & nmask) * (uint32_t)kEpiBox;
       int ncols = e.block_n - j * 64; if (ncols > 64) ncols = 64;
       const int c0 = half * 32;
       const int ch = nt * e.block_n + j * 64 + c0;
@@ -188,7 +195,7 @@ __device__ __forceinline__ void epilogue_tma(const EpiArgs& e, const CUtensorMap
           }
         }
         uint32_t bits = 0u;
-        if (e.aux_mode == 3) {  // one Philox call per 128 channels of a row
+        if constexpr (kEpi == kEpiPhilox) {  // one Philox call per 128 channels of a row
           const unsigned long long el = e_row + (unsigned long long)ch;
           const unsigned long long ctr = (el >> 7) + rng_off;
           if (ctr != rnd_ctr) {
@@ -209,13 +216,13 @@ __device__ __forceinline__ void epilogue_tma(const EpiArgs& e, const CUtensorMap
             pk[2 * i + 1] = pack_bf16x2(__uint_as_float(v[4 * i + 2]) + b4[i].z, __uint_as_float(v[4 * i + 3]) + b4[i].w);
           }
           if (e.relu) epi_relu16(pk);
-          if (e.aux_mode == 3) {
+          if constexpr (kEpi == kEpiPhilox) {
             epi_dropout16(pk, bits);
-          } else if (aux_tma) {
+          } else if constexpr (aux_tma) {
             const __nv_bfloat162 z = u32_as_bf162(0u);
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
-              const uint4 a4 = *reinterpret_cast<const uint4*>(sb + chunk[g]);
+              const uint4 a4 = ld_shared_v4(sb_s + chunk[g]);
               const uint32_t au[4] = {a4.x, a4.y, a4.z, a4.w};
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
@@ -224,7 +231,7 @@ __device__ __forceinline__ void epilogue_tma(const EpiArgs& e, const CUtensorMap
               }
             }
           }
-          if (e.pool_out) {
+          if constexpr (kEpi == kEpiPool) {
             // fused 2x2 max-pool: no staging box, no TMA store — the pooled quarter of each window goes straight out
             uint32_t m[4];
             const uint32_t bits = epi_pool2x2(pk, lane, m);
@@ -237,41 +244,9 @@ __device__ __forceinline__ void epilogue_tma(const EpiArgs& e, const CUtensorMap
               if (e.pool_idx) e.pool_idx[pp * (e.cout >> 3) + (c >> 3)] = (unsigned short)bits;
             }
           }
-          if (!e.pool_out || e.pool_keep_full) {
+          if (kEpi != kEpiPool || e.pool_keep_full) {
 #pragma unroll
-          for (int g = 0; g < 4; ++g)
-            *reinterpret_cast<uint4*>(sb + chunk[g]) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
-          }
-          if (e.unpool_out) {
-            // fused max-pool backward: this row is a POOLED pixel; its (already ReLU-masked) gradient goes to the
-            // arg-max position of its 2 x 2 window of the full-resolution gradient, zeros to the other three.  The
-            // staged copy above only feeds the column sums; it is not stored.
-            const int px = w0 + r_w, py = h0 + r_h;
-            if (px < e.out_W && py < e.out_H) {
-              const size_t pp = ((size_t)(n0 + r_n) * e.out_H + py) * e.out_W + px;
-              const uint2 ib = __ldg(reinterpret_cast<const uint2*>(e.unpool_idx + pp * (e.cout >> 3) + (ch >> 3)));
-              const size_t fw = (size_t)e.out_W * 2;
-              bf16* o00 = e.unpool_out + (((size_t)(n0 + r_n) * e.out_H * 2 + 2 * py) * fw + 2 * px) * e.unpool_cs +
-                          e.unpool_coff + ch;
-#pragma unroll
-              for (int pos = 0; pos < 4; ++pos) {
-                uint4* op = reinterpret_cast<uint4*>(o00 + ((size_t)(pos >> 1) * fw + (pos & 1)) * e.unpool_cs);
-#pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                  const uint32_t b16 = ((g < 2 ? ib.x : ib.y) >> (16 * (g & 1))) & 0xFFFFu;  // 2 arg bits x 8 channels
-                  const uint32_t x = b16 ^ (uint32_t)(pos * 0x5555);
-                  const uint32_t z = ~(x | (x >> 1)) & 0x5555u;                               // bit 2j: channel j hit
-                  uint32_t w[4];
-#pragma unroll
-                  for (int i = 0; i < 4; ++i) {
-                    const uint32_t t = z >> (4 * i);
-                    const uint32_t m = ((0u - (t & 1u)) & 0x0000FFFFu) | ((0u - ((t >> 2) & 1u)) & 0xFFFF0000u);
-                    w[i] = pk[4 * g + i] & m;
-                  }
-                  op[g] = make_uint4(w[0], w[1], w[2], w[3]);
-                }
-              }
-            }
+          for (int g = 0; g < 4; ++g) st_shared_v4(sb_s + chunk[g], pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
           }
         }
       } else {
@@ -293,11 +268,11 @@ __device__ __forceinline__ void epilogue_tma(const EpiArgs& e, const CUtensorMap
             }
             uint4* s0 = reinterpret_cast<uint4*>(sb + row_off + ((((c >> 3)) ^ sw) << 4));
             uint4* s1 = reinterpret_cast<uint4*>(sb + row_off + ((((c >> 3) + 1) ^ sw) << 4));
-            if (e.aux_mode == 3) {
+            if constexpr (kEpi == kEpiPhilox) {
               const uint32_t bits = dropout_bits16(e_row + (unsigned long long)chc, rng_seed, rng_off);
 #pragma unroll
               for (int i = 0; i < 16; ++i) f[i] = ((bits >> i) & 1u) ? f[i] * 2.f : 0.f;
-            } else if (aux_tma) {
+            } else if constexpr (aux_tma) {
               const uint4 a0 = *s0, a1 = *s1;
               const uint32_t au[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
 #pragma unroll
@@ -319,7 +294,7 @@ __device__ __forceinline__ void epilogue_tma(const EpiArgs& e, const CUtensorMap
           }
         }
       }
-      if (e.pool_out && !e.pool_keep_full) continue;  // nothing staged, nothing to store (whole 64-column blocks only)
+      if (kEpi == kEpiPool && !e.pool_keep_full) continue;  // nothing staged, nothing to store (whole 64-column blocks only)
       fence_proxy_async_smem();
       if (leader) {
         // Before the barrier of sub-block q the leader proves free the box that is written next: the box of
@@ -334,7 +309,7 @@ __device__ __forceinline__ void epilogue_tma(const EpiArgs& e, const CUtensorMap
         }
       }
       named_bar_sync(1, 256);
-      if (leader && !e.unpool_out) {
+      if (leader) {
         tma_store_4d(tmO, sb, nt * e.block_n + j * 64, w0, h0, n0);
         bulk_commit();
       }

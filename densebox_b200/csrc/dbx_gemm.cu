@@ -175,14 +175,14 @@ struct FpropParams {
   int cta2;                // 1: CTA pairs drive tcgen05.mma.cta_group::2 (launched with cluster size 2)
   int tma_epi, nbuf, nbuf_log2, nsb;  // bf16 outputs: epilogue staged through `nbuf` (2/4/8) smem boxes, `nsb` 64-column blocks/tile
   bf16* pool_out; int pool_cs, pool_coff; unsigned short* pool_idx; int pool_keep_full;  // fused 2x2 max-pool (ConvEpilogue)
-  bf16* unpool_out; int unpool_cs, unpool_coff; const unsigned short* unpool_idx;        // fused max-pool backward
 };
 
 // kMode: 1 / 2 / 4 = K blocks (one tap x 64 channels) per pipeline stage; 3 = column-box mode for 3x3 pad-1 layers:
 // 8 x 16 pixel tiles, ONE 8 x 18 input box per (filter column s, channel slice) serves the three filter rows (a row
 // shift = 8 pixels = one 1024-B swizzle atom, so the descriptor just starts r atoms further) and travels with its
 // three filter tiles behind one barrier: 12 MMAs per barrier round trip, A traffic 3 x 18 KB instead of 9 x 16 KB.
-template <bool kCta2, int kMode>
+// kEpi: epilogue flavour (dbx_epilogue.cuh), chosen by the launcher from ConvEpilogue.
+template <bool kCta2, int kMode, int kEpi>
 __global__ void __launch_bounds__(kFpropThreads, 1)
 conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmX,
@@ -401,7 +401,6 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       ea.csum = csum;
       ea.pool_out = p.pool_out; ea.pool_cs = p.pool_cs; ea.pool_coff = p.pool_coff; ea.pool_idx = p.pool_idx;
       ea.pool_keep_full = p.pool_keep_full;
-      ea.unpool_out = p.unpool_out; ea.unpool_cs = p.unpool_cs; ea.unpool_coff = p.unpool_coff; ea.unpool_idx = p.unpool_idx;
       const int my_tiles = u0 < total ? (total - 1 - u0) / ustep + 1 : 0;
       auto tile_of = [&](int it, int& nt, int& w0, int& h0, int& n0) {
         DBX_UNIT_TILE(u0 + it * ustep, nt_, mt_);
@@ -409,7 +408,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         DBX_TILE_ORIGIN(mt_, twi, thi, tni);
         w0 = twi * p.tw; h0 = thi * p.th; n0 = tni * p.tn;
       };
-      epilogue_tma<cta2>(ea, &tmO, &tmX, smem + (size_t)p.stages * stage_bytes, aux_bar, tfull_bar, tempty_bar, tmem,
+      epilogue_tma<cta2, kEpi>(ea, &tmO, &tmX, smem + (size_t)p.stages * stage_bytes, aux_bar, tfull_bar, tempty_bar, tmem,
                          my_tiles, tile_of);
     } else {
       const int q = warp & 3, half = (warp - 2) >> 2;
@@ -503,30 +502,8 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 }
 
 
-static int conv_fprop_impl(const Act& x, const void* wk, int R, int S, int pad, const Act& out, const ConvEpilogue& epi,
-                           int block_n, cudaStream_t stream, bool* unpool_fused);
-
 int conv_fprop(const Act& x, const void* wk, int R, int S, int pad, const Act& out, const ConvEpilogue& epi,
                int block_n, cudaStream_t stream) {
-  if (!epi.unpool_out) return conv_fprop_impl(x, wk, R, S, pad, out, epi, block_n, stream, nullptr);
-  // fused max-pool backward wanted: try it; if the launch cannot fuse (tile shape, no room for the column sums),
-  // fall back to the plain data gradient followed by the stand-alone un-pooling kernel
-  if (epi.aux_mode != 1 || !epi.aux || !epi.unpool_idx) return DBX_ERR_ARG;
-  bool fused = false;
-  int rc = conv_fprop_impl(x, wk, R, S, pad, out, epi, block_n, stream, &fused);
-  if (rc || fused) return rc;
-  ConvEpilogue plain = epi;
-  plain.aux = nullptr; plain.aux_mode = 0; plain.aux_cs = 0; plain.aux_coff = 0; plain.colsum = nullptr;
-  plain.unpool_out = nullptr; plain.unpool_idx = nullptr;
-  rc = conv_fprop_impl(x, wk, R, S, pad, out, plain, block_n, stream, nullptr);
-  if (rc) return rc;
-  Act p = out; p.ptr = const_cast<void*>(epi.aux); p.cs = epi.aux_cs; p.coff = epi.aux_coff;
-  Act dy = out; dy.ptr = epi.unpool_out; dy.H = out.H * 2; dy.W = out.W * 2; dy.cs = epi.unpool_cs; dy.coff = epi.unpool_coff;
-  return maxpool2x2_bwd_idx(p, out, epi.unpool_idx, dy, stream, epi.colsum);
-}
-
-static int conv_fprop_impl(const Act& x, const void* wk, int R, int S, int pad, const Act& out, const ConvEpilogue& epi,
-                           int block_n, cudaStream_t stream, bool* unpool_fused) {
   if (!x.ptr || !wk || !out.ptr) return DBX_ERR_ARG;
   if (x.C % 64 || out.C % 16) return DBX_ERR_ARG;
   if (out.H != x.H + 2 * pad - R + 1 || out.W != x.W + 2 * pad - S + 1 || out.N != x.N) return DBX_ERR_ARG;
@@ -534,6 +511,7 @@ static int conv_fprop_impl(const Act& x, const void* wk, int R, int S, int pad, 
   if (out.cs % out_align || out.coff % out_align) return DBX_ERR_ARG;
   if ((epi.aux_mode == 1 || epi.aux_mode == 2) && (!epi.aux || epi.aux_cs % 8 || epi.aux_coff % 8)) return DBX_ERR_ARG;
   if (epi.aux_mode == 3 && (!epi.rng || epi.rng_channels % 128)) return DBX_ERR_ARG;
+  if (epi.aux_mode < 0 || epi.aux_mode > 3) return DBX_ERR_ARG;
   if (R == 3 && S == 3 && pad == 1 && x.C == 64 && out.C == 64 && !epi.out_fp32 && block_n <= 0 &&
       (epi.aux_mode == 1 || epi.aux_mode == 2)) {  // masked epilogue (conv1_2 dgrad); without a mask colbox + CTA pairs wins
     const char* e = ab_env("DBX_HALO");
@@ -675,25 +653,23 @@ static int conv_fprop_impl(const Act& x, const void* wk, int R, int S, int pad, 
     }
   }
 
-  if (epi.unpool_out) {
-    const bool ok = colbox && tma_epi && epi.aux_mode == 1 && block_n % 64 == 0 && out.C % 64 == 0 &&
-                    epi.unpool_cs % 8 == 0 && epi.unpool_coff % 8 == 0 && (!epi.colsum || p.colsum) && !pool_after &&
-                    !epi.pool_out;
-    if (!ok) { if (unpool_fused) *unpool_fused = false; return DBX_OK; }  // nothing launched: the caller falls back
-    p.unpool_out = (bf16*)epi.unpool_out; p.unpool_cs = epi.unpool_cs; p.unpool_coff = epi.unpool_coff;
-    p.unpool_idx = (const unsigned short*)epi.unpool_idx;
-    if (unpool_fused) *unpool_fused = true;
-  }
-
   if (p.kps == 3) p.kps = 2;
   typedef void (*FpropFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const FpropParams);
-  static const FpropFn fns[2][4] = {
-      {conv_fprop_kernel<false, 1>, conv_fprop_kernel<false, 2>, conv_fprop_kernel<false, 4>, conv_fprop_kernel<false, 3>},
-      {conv_fprop_kernel<true, 1>, conv_fprop_kernel<true, 2>, conv_fprop_kernel<true, 4>, conv_fprop_kernel<true, 3>}};
-  static SmemAttrOnce attr_once[2][4];
+#define DBX_FPROP_ROW(c2, e) \
+  {conv_fprop_kernel<c2, 1, e>, conv_fprop_kernel<c2, 2, e>, conv_fprop_kernel<c2, 4, e>, conv_fprop_kernel<c2, 3, e>}
+  static const FpropFn fns[4][2][4] = {
+      {DBX_FPROP_ROW(false, kEpiPlain), DBX_FPROP_ROW(true, kEpiPlain)},
+      {DBX_FPROP_ROW(false, kEpiMask), DBX_FPROP_ROW(true, kEpiMask)},
+      {DBX_FPROP_ROW(false, kEpiPhilox), DBX_FPROP_ROW(true, kEpiPhilox)},
+      {DBX_FPROP_ROW(false, kEpiPool), DBX_FPROP_ROW(true, kEpiPool)}};
+#undef DBX_FPROP_ROW
+  static SmemAttrOnce attr_once[4][2][4];
   const int fa = cta2 ? 1 : 0, fb = colbox ? 3 : (p.kps == 4 ? 2 : (p.kps == 2 ? 1 : 0));
-  const FpropFn fn = fns[fa][fb];
-  { const int arc = set_max_smem_once((const void*)fn, kSmemBudget + 1024, &attr_once[fa][fb]); if (arc) return arc; }
+  // epilogue flavour (the direct fp32 / DBX_DIRECT_EPI epilogue ignores it).  The pool test comes first: a pooled
+  // launch has no mask (checked above).
+  const int fe = p.pool_out ? kEpiPool : (epi.aux_mode == 3 ? kEpiPhilox : (epi.aux_mode ? kEpiMask : kEpiPlain));
+  const FpropFn fn = fns[fe][fa][fb];
+  { const int arc = set_max_smem_once((const void*)fn, kSmemBudget + 1024, &attr_once[fe][fa][fb]); if (arc) return arc; }
   const size_t smem = (size_t)p.stages * stage_bytes + ring + (p.colsum ? (size_t)8 * out.C * 4 : 0) + 1024;
   cudaLaunchConfig_t cfg{};
   cfg.blockDim = dim3(kFpropThreads);

@@ -381,14 +381,11 @@ struct Net {
   // bias_below: the group whose bias gradient is the column sum of dx (dx = dZ of that layer): produced by this
   // launch's epilogue (ConvEpilogue::colsum) instead of a separate pass over dx; the matching wgrad() call then
   // passes bias_done = true.
-  // unpool / unpool_idx: dx is the gradient of a POOLED map (relu_y = that pooled activation): store its 2x2 un-pooling
-  // into *unpool instead (ConvEpilogue::unpool_out) — the max-pool backward rides in this launch's epilogue.
   int dgrad(const Act& dy, const char* grp, int R, int pad, const Act& dx, const Act* relu_y, cudaStream_t st,
-            const char* bias_below = nullptr, const Act* unpool = nullptr, const void* unpool_idx = nullptr) {
+            const char* bias_below = nullptr) {
     ConvEpilogue e;
     if (relu_y) { e.aux = relu_y->ptr; e.aux_cs = relu_y->cs; e.aux_coff = relu_y->coff; e.aux_mode = 1; }
     if (bias_below) e.colsum = gb_of(bias_below);
-    if (unpool) { e.unpool_out = unpool->ptr; e.unpool_cs = unpool->cs; e.unpool_coff = unpool->coff; e.unpool_idx = unpool_idx; }
     DBX_K((std::string("dgrad:") + grp).c_str(), 2.0 * pixels(dy) * macs_of(grp),
           conv_fprop(dy, wd_of(grp), R, R, R - 1 - pad, dx, e, 0, st));
     return DBX_OK;
@@ -578,13 +575,6 @@ struct Net {
     // pass on the side stream, so their bias gradients stay with wgrad().  DBX_FUSE_BIAS_SHORT=1 fuses them too.
     bool fuse_short = false;
     { const char* e = ab_env("DBX_FUSE_BIAS_SHORT"); if (e && e[0] == '1') fuse_short = fuse; }
-    // pool1 / pool2 backward inside the epilogues of the conv2_1 / conv3_1 data gradients (ConvEpilogue::unpool_out):
-    // implemented, bit-identical (tests/test_gpu_fused_bias.py) and OFF by default — measured 0.306 ms for the two
-    // fused launches against 0.218 ms for dgrad + maxpool2x2_bwd_idx: the un-pooled tile leaves the epilogue as
-    // 16-byte stores to 32 different lines per instruction (a lane owns a pixel), 4 096 store wavefronts per tile,
-    // while the stand-alone kernel writes whole rows.  DBX_POOL_BWD_FUSE=1 enables it (A/B).
-    bool pool_bwd_fuse = false;
-    { const char* e = ab_env("DBX_POOL_BWD_FUSE"); if (e && e[0] == '1') pool_bwd_fuse = pool_idx; }
     const int h2 = H / 2, w2 = W / 2, h4 = H / 4, w4 = W / 4, h8 = H / 8, w8 = W / 8;
     Act col0 = act("col0", H, W, 64), a11 = act("a11", H, W, 64), a12 = act("a12", H, W, 64);
     Act p1 = act("p1", h2, w2, 64), a21 = act("a21", h2, w2, 128), a22 = act("a22", h2, w2, 128);
@@ -666,23 +656,19 @@ struct Net {
     DBX_TRY(wgrad(a31, d_a32, "conv3_2", 3, 1, st, fuse));
     DBX_TRY(dgrad(d_a32, "conv3_2", 3, 1, d_a31, &a31, st, fuse ? "conv3_1" : nullptr));
     DBX_TRY(wgrad(p2, d_a31, "conv3_1", 3, 1, st, fuse));
-    if (pool_bwd_fuse) DBX_TRY(dgrad(d_a31, "conv3_1", 3, 1, d_p2, &p2, st, fuse ? "conv2_2" : nullptr, &d_a22, buf("pi2")));
-    else DBX_TRY(dgrad(d_a31, "conv3_1", 3, 1, d_p2, nullptr, st));
+    DBX_TRY(dgrad(d_a31, "conv3_1", 3, 1, d_p2, nullptr, st));
     if (stage == 1) return join_side(st);
     }
     // conv2 block
     // pool2 / pool1 backward read the pooled map + the 2-bit arg-max map of the forward pass instead of a22 / a12
-    if (pool_bwd_fuse) {}
-    else if (pool_idx) DBX_K("pool_bwd", 0.0, maxpool2x2_bwd_idx(p2, d_p2, buf("pi2"), d_a22, st, fuse ? gb_of("conv2_2") : nullptr));
+    if (pool_idx) DBX_K("pool_bwd", 0.0, maxpool2x2_bwd_idx(p2, d_p2, buf("pi2"), d_a22, st, fuse ? gb_of("conv2_2") : nullptr));
     else DBX_K("pool_bwd", 0.0, maxpool2x2_bwd(a22, d_p2, nullptr, d_a22, st, fuse ? gb_of("conv2_2") : nullptr));
     DBX_TRY(wgrad(a21, d_a22, "conv2_2", 3, 1, st, fuse));
     DBX_TRY(dgrad(d_a22, "conv2_2", 3, 1, d_a21, &a21, st, fuse_short ? "conv2_1" : nullptr));
     DBX_TRY(wgrad(p1, d_a21, "conv2_1", 3, 1, st, fuse_short));
-    if (pool_bwd_fuse) DBX_TRY(dgrad(d_a21, "conv2_1", 3, 1, d_p1, &p1, st, fuse ? "conv1_2" : nullptr, &d_a12, buf("pi1")));
-    else DBX_TRY(dgrad(d_a21, "conv2_1", 3, 1, d_p1, nullptr, st));
+    DBX_TRY(dgrad(d_a21, "conv2_1", 3, 1, d_p1, nullptr, st));
     // conv1 block
-    if (pool_bwd_fuse) {}
-    else if (pool_idx) DBX_K("pool_bwd", 0.0, maxpool2x2_bwd_idx(p1, d_p1, buf("pi1"), d_a12, st, fuse ? gb_of("conv1_2") : nullptr));
+    if (pool_idx) DBX_K("pool_bwd", 0.0, maxpool2x2_bwd_idx(p1, d_p1, buf("pi1"), d_a12, st, fuse ? gb_of("conv1_2") : nullptr));
     else DBX_K("pool_bwd", 0.0, maxpool2x2_bwd(a12, d_p1, nullptr, d_a12, st, fuse ? gb_of("conv1_2") : nullptr));
     DBX_TRY(wgrad(a11, d_a12, "conv1_2", 3, 1, st, fuse));
     DBX_TRY(dgrad(d_a12, "conv1_2", 3, 1, d_a11, &a11, st, (fuse_short && !pairs) ? "conv1_1" : nullptr));

@@ -165,36 +165,3 @@ def test_pool_fused_into_conv_epilogue_matches_separate_pool_kernel():
     assert L_a == L_b
     for n in g_a:
         assert (g_a[n] - g_b[n]).abs().max().item() <= 1e-4 * g_a[n].abs().max().item() + 1e-30, n
-
-
-def _bwd_buffers(fuse_bwd):
-    from densebox_b200 import densebox_loss
-    os.environ["DBX_POOL_BWD_FUSE"] = "1" if fuse_bwd else "0"
-    try:
-        _, net = build("densebox")
-        net = net.cuda().eval()
-        x, lab, rand, _ = make_inputs(3, "densebox")
-        score, loc = net(x.cuda())
-        L = densebox_loss(score, loc, lab["bbox"], rand_neg_idx=rand)
-        L.backward()
-        torch.cuda.synchronize()
-        eng = next(iter(net._engines.values()))
-        bufs = [eng.buffer("d_a12", torch.bfloat16).clone(), eng.buffer("d_a22", torch.bfloat16).clone()]
-        g = {n: p.grad.detach().float().cpu() for n, p in net.named_parameters() if p.grad is not None}
-        return bufs, g
-    finally:
-        os.environ.pop("DBX_POOL_BWD_FUSE", None)
-
-
-def test_pool_backward_fused_into_dgrad_epilogue_matches_separate_kernel():
-    """pool1 / pool2 backward computed inside the epilogues of the conv2_1 / conv3_1 data gradients (d_p1 / d_p2 never
-    reach HBM) against dgrad + maxpool2x2_bwd_idx_kernel: the full-resolution gradients d_a12 / d_a22 bit-identical,
-    every parameter gradient (incl. the conv1_2 / conv2_2 bias gradients, which come out of the same epilogue) equal up
-    to the summation order of the atomics."""
-    bufs_a, g_a = _bwd_buffers(False)
-    bufs_b, g_b = _bwd_buffers(True)
-    for a, b in zip(bufs_a, bufs_b):
-        assert torch.equal(a, b)
-        assert a.float().abs().max().item() > 0
-    for n in g_a:
-        assert (g_a[n] - g_b[n]).abs().max().item() <= 1e-4 * g_a[n].abs().max().item() + 1e-30, n
