@@ -161,7 +161,10 @@ int dbx_net_refresh_dgrad(void* handle, void* stream);
  * dropout_mode 0 = eval(); 1 = train(), nn.Dropout drawn inside the conv epilogues from Philox(seed, offset);
  * 2 = train() with the {0,2} bf16 mask the caller has written into the "drop" region (parity tests inject the
  * oracle's mask); 3 = like 1 but {seed, offset} are read from the "rng" region (2 x u64) as the caller left it
- * (CUDA-graph replays). */
+ * (CUDA-graph replays).
+ * A net created with train = 0 (no backward pass, dropout_mode must be 0) computes the head maps through ONE folded
+ * 768 -> C matrix per forward: nothing but Dropout sits between conv5_1_* and conv5_2_* (DenseBox.py:158-178), so in
+ * eval mode their product is the same linear map; the "hd" region is not written by such a net. */
 int dbx_net_forward(void* handle, const float* x, int dropout_mode, unsigned long long seed,
                     unsigned long long offset, void* stream);
 
